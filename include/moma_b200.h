@@ -1,0 +1,178 @@
+/* moma_b200 -- C ABI of the B200 (sm_100a) MoMA criterion hot path.
+ *
+ * The reference (trinhvg/MoMA) has no FFI: its operator interface is the Python
+ * module API (MoMA/mem_moco.py, MoMA/criterion_moco_att.py,
+ * learning/contrast_trainer.py).  This header is the boundary a binding for that
+ * API calls into; every entry point names the reference lines it replaces.
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers, sizes, scalars, a CUDA stream; no torch types.
+ *   - every buffer (inputs, outputs, workspaces, the queue and its bf16 shadow)
+ *     is allocated and owned by the caller; the library never allocates or frees
+ *     device memory and keeps no pointer past the call.
+ *   - all work is enqueued asynchronously on `stream`; no device sync inside.
+ *   - return value: MOMA_OK (0) or a negative moma_status; moma_last_error()
+ *     returns a thread-local message for the last failure on this thread.
+ *   - row-major, fp32 unless a `dtype` argument says otherwise; 16-byte aligned
+ *     base pointers and row strides (D % 4 == 0 for fp32, D % 8 == 0 for bf16).
+ *   - there is NO CPU fallback: on a machine without a CUDA device every compute
+ *     entry point fails with MOMA_ERR_CUDA.
+ */
+#ifndef MOMA_B200_H_
+#define MOMA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOMA_ABI_VERSION 1
+
+typedef void *moma_stream_t; /* cudaStream_t / CUstream */
+
+enum moma_status {
+    MOMA_OK = 0,
+    MOMA_ERR_INVALID = -1,     /* bad argument (null pointer, non-positive size, n > K ...) */
+    MOMA_ERR_ALIGN = -2,       /* pointer / row stride not 16-byte aligned */
+    MOMA_ERR_UNSUPPORTED = -3, /* shape outside the kernels' supported set */
+    MOMA_ERR_CUDA = -4,        /* CUDA runtime / launch error, or no device */
+    MOMA_ERR_WORKSPACE = -5    /* caller-provided workspace too small */
+};
+
+enum moma_dtype { MOMA_F32 = 0, MOMA_BF16 = 1 };
+
+int moma_abi_version(void);
+const char *moma_last_error(void);
+/* 1 when the library was built with the tcgen05/TMA InfoNCE kernel and a device
+ * of compute capability 10.x is present. */
+int moma_has_tcgen05(void);
+
+/* ------------------------------------------------------------------------- *
+ * (c) momentum-encoder EMA
+ * replaces learning/contrast_trainer.py:207-211 (momentum_update):
+ *     for p1, p2 in zip(model.parameters(), model_ema.parameters()):
+ *         p2.data.mul_(m).add_(p1.detach().data, alpha=(1 - m))
+ * One launch for the whole parameter list.  Arithmetic is exactly the
+ * reference's two fp32 roundings: t = fl(p2*m); p2 = fl(fma(alpha, p1, t)).
+ *
+ * A "plan" is a caller-owned table describing the tensor list, cut into
+ * chunks.  Build it once per (model, model_ema) pair:
+ *   1. moma_ema_plan_size   -> number of chunks and table size in bytes
+ *   2. moma_ema_plan_fill   -> fill a HOST table (caller copies it to the device)
+ *   3. moma_ema_multi       -> every step, with the DEVICE copy of the table
+ * ------------------------------------------------------------------------- */
+int moma_ema_plan_size(int n_tensors, const int64_t *numels, int64_t *n_chunks, size_t *table_bytes);
+int moma_ema_plan_fill(int n_tensors, const void *const *src_ptrs, void *const *dst_ptrs,
+                       const int64_t *numels, void *host_table, size_t table_bytes);
+int moma_ema_multi(const void *dev_table, int64_t n_chunks, float m, float one_minus_m,
+                   moma_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * (c) Normalize -- replaces MoMA/criterion_moco_att.py:12-18
+ *     F.normalize(x, p=2, dim=1) = x / max(||x||_2, eps)      (and its backward)
+ * ------------------------------------------------------------------------- */
+int moma_l2norm_fwd(const float *x, float *y, int64_t rows, int64_t D, float eps,
+                    moma_stream_t stream);
+int moma_l2norm_bwd(const float *x, const float *grad_y, float *grad_x, int64_t rows, int64_t D,
+                    float eps, moma_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * (c) ring enqueue + pointer -- replaces MoMA/mem_moco.py:14-27
+ *     ids = fmod(arange(n) + index, K).long(); queue.index_copy_(0, ids, k)
+ *     index = (index + n) % K
+ * `K` is the GLOBAL queue length.  With shard_world > 1 the queue is sharded
+ * cyclically by row: global row g lives on rank g % shard_world at local slot
+ * g / shard_world, `queue_f32`/`queue_bf16` point at this rank's shard
+ * [K / shard_world, D], and only owned rows are written (K % shard_world == 0).
+ * `queue_bf16` (nullable) is the bf16 shadow read by the tensor-core kernel.
+ * `index_dev` (nullable) overrides `index` with a device-resident int64 so the
+ * step is CUDA-graph capturable; moma_pointer_advance updates it on the stream.
+ * normalize != 0 fuses Normalize (above) into the copy.
+ * n > K is rejected (the reference's behaviour is undefined there).
+ * ------------------------------------------------------------------------- */
+int moma_enqueue(const float *keys, int64_t n, int64_t D, float *queue_f32, void *queue_bf16,
+                 int64_t K, int64_t index, const int64_t *index_dev, int shard_rank,
+                 int shard_world, int normalize, float eps, moma_stream_t stream);
+int moma_enqueue_ids(int64_t n, int64_t index, const int64_t *index_dev, int64_t K,
+                     int64_t *out_ids, moma_stream_t stream);
+int moma_pointer_advance(int64_t *index_dev, int64_t n, int64_t K, moma_stream_t stream);
+/* fp32 -> bf16 (round to nearest even); used to (re)build the queue shadow. */
+int moma_cast_bf16(const float *src, void *dst_bf16, int64_t numel, moma_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * (a) InfoNCE logits + cross-entropy forward AND backward in one pass
+ * replaces MoMA/mem_moco.py:29-49 (_compute_logit), :89 (queue clone),
+ * learning/contrast_trainer.py:189-205 (CrossEntropyLoss + top-1 accuracy) and
+ * the autograd backward of those ops.  The [B, K+1] logits never reach HBM.
+ *
+ * Stage 1, moma_nce_partial: for each of `n_splits` contiguous slices of the
+ * local queue rows, per query row i
+ *     m_i = reference max, l_i = sum_j exp(s_ij - m_i), O_i = sum_j exp(s_ij - m_i) queue_j,
+ *     mmax_i = true max_j s_ij,            s_ij = q_i . queue_j / T
+ * written to part_m/part_l/part_mmax [n_splits, B] and part_O [n_splits, B, D] (fp32).
+ *   dtype MOMA_F32 : q, queue fp32; SIMT FFMA kernel (1e-5 parity mode)
+ *   dtype MOMA_BF16: q, queue bf16; tcgen05/TMEM kernel fed by TMA
+ * Stage 2, moma_nce_combine: merges `n_parts` partials (splits x shards), adds
+ * the positive column q_i.k_i/T and emits
+ *     loss_rows[i] = LSE_i - l_i0,   dq_unit[i,:] = (sum_j p_ij c_j - k_i)/T,
+ *     pos_is_max[i] = (l_i0 >= max_j l_ij)      (top-1 accuracy by-product)
+ * The caller applies the 1/B of CrossEntropyLoss's mean and the upstream grad.
+ * q_f32/kpos_f32 are fp32 (in bf16 mode: the bf16-rounded values widened).
+ * ------------------------------------------------------------------------- */
+int moma_nce_num_splits(int64_t B, int64_t D, int64_t K_local, int dtype);
+int moma_nce_partial(const void *q, const void *queue, int64_t B, int64_t D, int64_t K_local,
+                     float inv_T, int dtype, int n_splits, float *part_m, float *part_l,
+                     float *part_mmax, float *part_O, moma_stream_t stream);
+int moma_nce_combine(const float *part_m, const float *part_l, const float *part_mmax,
+                     const float *part_O, int n_parts, const float *q_f32, const float *kpos_f32,
+                     int64_t B, int64_t D, float inv_T, float *loss_rows, float *dq_unit,
+                     int32_t *pos_is_max, float *max_logit /* nullable: max_j l_ij */,
+                     moma_stream_t stream);
+/* Escape hatch / tests: materialise logits[B, K+1] = cat(q.k, q queue^T) / T
+ * exactly as mem_moco.py:29-49 lays them out (row stride K+1). */
+int moma_nce_logits(const void *q, const void *kpos, const void *queue, int64_t B, int64_t D,
+                    int64_t K, float T, int dtype, float *logits, moma_stream_t stream);
+/* positives only: mem_moco.py:51-66 (_compute_logit_qk) -> out[B] */
+int moma_nce_logits_qk(const float *q, const float *kpos, int64_t B, int64_t D, float T,
+                       float *out, moma_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * (b) multi-head attention over the batch axis
+ * replaces MoMA/criterion_moco_att.py:153-167 (Attention.forward):
+ *     qkv = x W_qkv^T + b_qkv; attn = softmax(q k^T * hd^-0.5); y = (attn v) W_proj^T + b_proj
+ * x [N, C]; w_qkv [3C, C]; b_qkv [3C] or NULL; w_proj [C, C]; b_proj [C].
+ * Saved for backward (caller-owned): qkv [N, 3C], o [N, C] (merged heads),
+ * lse [H, N].  attn_probs (nullable, [H, N, N]) is only for Attention_viz.
+ * head_dim = C / H must be one of 16, 32, 64, 128.
+ * ------------------------------------------------------------------------- */
+int moma_attn_fwd(const float *x, const float *w_qkv, const float *b_qkv, const float *w_proj,
+                  const float *b_proj, int64_t N, int64_t C, int H, float *y, float *qkv,
+                  float *o, float *lse, float *attn_probs, moma_stream_t stream);
+size_t moma_attn_bwd_workspace_bytes(int64_t N, int64_t C, int H);
+/* Any of the gradient outputs may be NULL (skipped). Gradients are overwritten,
+ * not accumulated. */
+int moma_attn_bwd(const float *x, const float *w_qkv, const float *w_proj, const float *qkv,
+                  const float *o, const float *lse, const float *grad_y, int64_t N, int64_t C,
+                  int H, float *grad_x, float *grad_w_qkv, float *grad_b_qkv, float *grad_w_proj,
+                  float *grad_b_proj, void *workspace, size_t workspace_bytes,
+                  moma_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * debug / test hooks (not used by the product path)
+ * moma_debug_nce_tc: the tcgen05 partial kernel with an optional dump of the raw
+ *   score tile S = Q . Tile^T of the first queue tile of split 0:
+ *   dbg_S [B, BN] (BN = 128, or 64 when D == 256), nullable.
+ * moma_debug_tc_error: synchronising read of the device-side protocol-error code
+ *   (a bounded mbarrier wait that timed out records which one and traps); 0 = none.
+ * ------------------------------------------------------------------------- */
+int moma_debug_nce_tc(const void *q, const void *queue, int64_t B, int64_t D, int64_t K_local,
+                      float inv_T, int n_splits, float *part_m, float *part_l, float *part_mmax,
+                      float *part_O, float *dbg_S, moma_stream_t stream);
+int moma_debug_tc_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOMA_B200_H_ */

@@ -1,0 +1,414 @@
+// InfoNCE logits + cross-entropy, FP32 parity path (SIMT FFMA) + combine + materialise.
+//
+// Replaces MoMA/mem_moco.py:29-49 (_compute_logit), the CrossEntropyLoss/top-1 at
+// learning/contrast_trainer.py:189-205 and their autograd backward.
+//
+// Algebra: labels are all zero, so with s_ij = q_i.queue_j / T
+//   loss_i = LSE_j(l_ij) - l_i0,   dloss_i/dq_i = (sum_j p_ij c_j - k_i) / T,
+// i.e. one flash-style pass over the queue yields both the LSE and P.queue.
+// moma_nce_partial produces per-(split) partials (m, l, O); moma_nce_combine
+// merges splits and shards, adds the positive column and emits loss rows + dq.
+//
+// The FP32 kernel here is the 1e-5-parity mode (no tensor cores: a single TF32
+// pass fails 1e-5 on the gradient).  The bf16 tensor-core
+// kernel lives in nce_tc.cu and shares the combine below.
+#include <math_constants.h>
+#include "common.cuh"
+
+namespace moma {
+
+int nce_tc_partial(const void* q, const void* queue, int64_t B, int64_t D, int64_t K_local,
+                   float inv_T, int n_splits, float* part_m, float* part_l, float* part_mmax,
+                   float* part_O, cudaStream_t stream);        // nce_tc.cu
+int nce_tc_num_splits(int64_t B, int64_t D, int64_t K_local);  // nce_tc.cu
+bool nce_tc_supported(int64_t B, int64_t D, int64_t K_local);  // nce_tc.cu
+
+// ------------------------------------------------------------------ fp32 partial
+// CTA = 256 threads = 8 warps; BM = 32 query rows (4 per warp), BN queue rows per
+// tile.  Q tile and queue tile live in shared memory with a +4 float row pad so
+// 128-bit row reads by consecutive lanes are bank-conflict free.
+constexpr int kBM = 32;
+constexpr int kSimtThreads = 256;
+
+template <int BN>   // 64 (D <= 256) or 32 (D <= 512)
+__global__ void __launch_bounds__(kSimtThreads)
+nce_partial_f32_kernel(const float* __restrict__ q, const float* __restrict__ queue, int B, int D,
+                       int64_t K, float inv_T, int n_splits, float* __restrict__ part_m,
+                       float* __restrict__ part_l, float* __restrict__ part_mmax,
+                       float* __restrict__ part_O) {
+    extern __shared__ __align__(16) float smem[];
+    const int ld = D + 4;
+    float* qs = smem;                       // [kBM][ld]
+    float* ks = qs + kBM * ld;              // [BN][ld]
+    float* ps = ks + BN * ld;               // [kBM][BN + 4]
+    constexpr int ldp = BN + 4;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = blockIdx.x * kBM;
+    const int split = blockIdx.y;
+    // split -> contiguous range of BN-row tiles
+    const int64_t n_tiles = (K + BN - 1) / BN;
+    const int64_t t_begin = n_tiles * split / n_splits;
+    const int64_t t_end = n_tiles * (split + 1) / n_splits;
+
+    const int nvec = D >> 2;
+    for (int i = tid; i < kBM * nvec; i += kSimtThreads) {
+        const int r = i / nvec, v = i - r * nvec;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m0 + r < B) a = reinterpret_cast<const float4*>(q + (int64_t)(m0 + r) * D)[v];
+        *reinterpret_cast<float4*>(qs + r * ld + 4 * v) = a;
+    }
+
+    // running stats for this warp's 4 rows (replicated across lanes)
+    float m_run[4], l_run[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { m_run[r] = -CUDART_INF_F; l_run[r] = 0.f; }
+    // O accumulators: 4 rows x (D/32) columns, column = lane + 32*c   (D <= 512 -> c < 16)
+    constexpr int kMaxC = 16;
+    float acc[4][kMaxC];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < kMaxC; ++c) acc[r][c] = 0.f;
+    const int ncol = (D + 31) >> 5;
+
+    for (int64_t t = t_begin; t < t_end; ++t) {
+        const int64_t j0 = t * BN;
+        __syncthreads();                                   // previous tile fully consumed
+        for (int i = tid; i < BN * nvec; i += kSimtThreads) {
+            const int r = i / nvec, v = i - r * nvec;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j0 + r < K) a = ld_stream(reinterpret_cast<const float4*>(queue + (j0 + r) * D) + v);
+            *reinterpret_cast<float4*>(ks + r * ld + 4 * v) = a;
+        }
+        __syncthreads();
+
+        // S[4 rows][BN/32 cols per lane]: column j = lane + 32*cc
+        constexpr int CC = BN / 32;
+        float s[4][CC];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int cc = 0; cc < CC; ++cc) s[r][cc] = 0.f;
+        for (int v = 0; v < nvec; ++v) {
+            float4 kk[CC];
+#pragma unroll
+            for (int cc = 0; cc < CC; ++cc)
+                kk[cc] = *reinterpret_cast<const float4*>(ks + (lane + 32 * cc) * ld + 4 * v);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float4 qq = *reinterpret_cast<const float4*>(qs + (warp * 4 + r) * ld + 4 * v);
+#pragma unroll
+                for (int cc = 0; cc < CC; ++cc)
+                    s[r][cc] += qq.x * kk[cc].x + qq.y * kk[cc].y + qq.z * kk[cc].z + qq.w * kk[cc].w;
+            }
+        }
+        // online softmax per row (warp-shuffle reductions)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            float mx = -CUDART_INF_F;
+#pragma unroll
+            for (int cc = 0; cc < CC; ++cc) {
+                s[r][cc] = (j0 + lane + 32 * cc < K) ? s[r][cc] * inv_T : -CUDART_INF_F;
+                mx = fmaxf(mx, s[r][cc]);
+            }
+            mx = warp_max(mx);
+            const float m_new = fmaxf(m_run[r], mx);
+            const float corr = (m_run[r] == -CUDART_INF_F) ? 0.f : expf(m_run[r] - m_new);
+            float sum = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < CC; ++cc) {
+                const float p = (s[r][cc] == -CUDART_INF_F) ? 0.f : expf(s[r][cc] - m_new);
+                ps[(warp * 4 + r) * ldp + lane + 32 * cc] = p;
+                sum += p;
+            }
+            sum = warp_sum(sum);
+            l_run[r] = l_run[r] * corr + sum;
+            m_run[r] = m_new;
+#pragma unroll
+            for (int c = 0; c < kMaxC; ++c)
+                if (c < ncol) acc[r][c] *= corr;
+        }
+        __syncwarp();
+        // O += P . tile
+        for (int j = 0; j < BN; j += 4) {
+            float4 p4[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                p4[r] = *reinterpret_cast<const float4*>(ps + (warp * 4 + r) * ldp + j);
+#pragma unroll
+            for (int c = 0; c < kMaxC; ++c) {
+                if (c < ncol) {
+                    const int col = lane + 32 * c;
+                    const bool ok = col < D;
+                    const float v0 = ok ? ks[(j + 0) * ld + col] : 0.f;
+                    const float v1 = ok ? ks[(j + 1) * ld + col] : 0.f;
+                    const float v2 = ok ? ks[(j + 2) * ld + col] : 0.f;
+                    const float v3 = ok ? ks[(j + 3) * ld + col] : 0.f;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        acc[r][c] += p4[r].x * v0 + p4[r].y * v1 + p4[r].z * v2 + p4[r].w * v3;
+                }
+            }
+        }
+    }
+
+    // write partials
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int row = m0 + warp * 4 + r;
+        if (row >= B) continue;
+        const int64_t o = (int64_t)split * B + row;
+        if (lane == 0) { part_m[o] = m_run[r]; part_l[o] = l_run[r]; part_mmax[o] = m_run[r]; }
+#pragma unroll
+        for (int c = 0; c < kMaxC; ++c) {
+            const int col = lane + 32 * c;
+            if (c < ncol && col < D) part_O[o * D + col] = acc[r][c];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ combine
+// One CTA of 128 threads per query row.
+__global__ void __launch_bounds__(128)
+nce_combine_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l,
+                   const float* __restrict__ part_mmax, const float* __restrict__ part_O,
+                   int n_parts, const float* __restrict__ q, const float* __restrict__ kpos, int B,
+                   int D, float inv_T, float* __restrict__ loss_rows, float* __restrict__ dq_unit,
+                   int32_t* __restrict__ pos_is_max, float* __restrict__ max_logit) {
+    __shared__ float red[4];
+    __shared__ float s_w[256];
+    const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* qr = q + (int64_t)row * D;
+    const float* kr = kpos + (int64_t)row * D;
+    float dot = 0.f;
+    for (int d = tid; d < D; d += 128) dot += qr[d] * kr[d];
+    dot = warp_sum(dot);
+    if (lane == 0) red[warp] = dot;
+    __syncthreads();
+    const float pos = (red[0] + red[1] + red[2] + red[3]) * inv_T;
+
+    float mref = -CUDART_INF_F, mtrue = -CUDART_INF_F;
+    for (int s = 0; s < n_parts; ++s) {
+        mref = fmaxf(mref, part_m[(int64_t)s * B + row]);
+        mtrue = fmaxf(mtrue, part_mmax[(int64_t)s * B + row]);
+    }
+    const float mstar = fmaxf(mref, pos);
+    const float wpos = expf(pos - mstar);
+
+    float l = wpos;
+    // D <= 128*4 handled with up to 4 columns per thread; larger D loops
+    for (int d0 = 0; d0 < D; d0 += 512) {
+        float o[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int d = d0 + tid + 128 * c;
+            o[c] = (d < D) ? wpos * kr[d] : 0.f;
+        }
+        for (int s0 = 0; s0 < n_parts; s0 += 256) {
+            const int cnt = min(256, n_parts - s0);
+            __syncthreads();
+            for (int s = tid; s < cnt; s += 128) {
+                const float ms = part_m[(int64_t)(s0 + s) * B + row];
+                s_w[s] = (ms == -CUDART_INF_F) ? 0.f : expf(ms - mstar);
+            }
+            __syncthreads();
+            for (int s = 0; s < cnt; ++s) {
+                const float w = s_w[s];
+                const int64_t base = ((int64_t)(s0 + s) * B + row);
+                if (d0 == 0 && tid == 0) l += w * part_l[base];
+                const float* Os = part_O + base * D;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int d = d0 + tid + 128 * c;
+                    if (d < D) o[c] += w * Os[d];
+                }
+            }
+        }
+        if (d0 == 0) {
+            __syncthreads();
+            if (tid == 0) red[0] = l;
+            __syncthreads();
+            l = red[0];
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int d = d0 + tid + 128 * c;
+            if (d < D) dq_unit[(int64_t)row * D + d] = (o[c] / l - kr[d]) * inv_T;
+        }
+    }
+    if (tid == 0) {
+        loss_rows[row] = logf(l) + mstar - pos;
+        pos_is_max[row] = (pos >= mtrue) ? 1 : 0;
+        if (max_logit) max_logit[row] = fmaxf(pos, mtrue);
+    }
+}
+
+// ------------------------------------------------------------------ materialise
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// logits[i, 1 + j] = q_i . queue_j / T ; 64x64 tile, 16-wide k-step, 4x4 per thread
+template <typename T>
+__global__ void __launch_bounds__(256)
+nce_logits_kernel(const T* __restrict__ q, const T* __restrict__ queue, int B, int D, int64_t K,
+                  float Tm, float* __restrict__ logits) {
+    __shared__ float qs[16][64 + 1];
+    __shared__ float ks[16][64 + 1];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * 64;
+    const int64_t n0 = (int64_t)blockIdx.x * 64;
+    float acc[4][4] = {};
+    for (int d0 = 0; d0 < D; d0 += 16) {
+        for (int i = tid; i < 64 * 16; i += 256) {
+            const int r = i >> 4, d = i & 15;
+            qs[d][r] = (m0 + r < B && d0 + d < D) ? to_f<T>(q[(int64_t)(m0 + r) * D + d0 + d]) : 0.f;
+            ks[d][r] = (n0 + r < K && d0 + d < D) ? to_f<T>(queue[(n0 + r) * D + d0 + d]) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int d = 0; d < 16; ++d) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = qs[d][ty + 16 * i]; b[i] = ks[d][tx + 16 * i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = m0 + ty + 16 * i;
+        if (r >= B) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t c = n0 + tx + 16 * j;
+            if (c < K) logits[(int64_t)r * (K + 1) + 1 + c] = acc[i][j] / Tm;
+        }
+    }
+}
+
+// column 0 (or the whole output of _compute_logit_qk): one warp per row
+template <typename T>
+__global__ void __launch_bounds__(128)
+nce_pos_kernel(const T* __restrict__ q, const T* __restrict__ kpos, int B, int D, float Tm,
+               float* __restrict__ out, int64_t out_stride) {
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= B) return;
+    float dot = 0.f;
+    for (int d = lane; d < D; d += 32)
+        dot += to_f<T>(q[(int64_t)row * D + d]) * to_f<T>(kpos[(int64_t)row * D + d]);
+    dot = warp_sum(dot);
+    if (lane == 0) out[(int64_t)row * out_stride] = dot / Tm;
+}
+
+static int partial_f32(const float* q, const float* queue, int64_t B, int64_t D, int64_t K,
+                       float inv_T, int n_splits, float* pm, float* pl, float* pmm, float* pO,
+                       cudaStream_t st) {
+    MOMA_REQUIRE(D % 4 == 0 && D <= 512, MOMA_ERR_UNSUPPORTED,
+                 "nce_partial(f32): D=%lld unsupported (need D %% 4 == 0, D <= 512); use moma_nce_logits",
+                 (long long)D);
+    const dim3 grid((unsigned)((B + kBM - 1) / kBM), (unsigned)n_splits);
+    const int ld = (int)D + 4;
+    if (D <= 256) {
+        constexpr int BN = 64;
+        const size_t smem = (size_t)(kBM * ld + BN * ld + kBM * (BN + 4)) * sizeof(float);
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(nce_partial_f32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = true; }
+        nce_partial_f32_kernel<BN><<<grid, kSimtThreads, smem, st>>>(q, queue, (int)B, (int)D, K, inv_T, n_splits, pm, pl, pmm, pO);
+    } else {
+        constexpr int BN = 32;
+        const size_t smem = (size_t)(kBM * ld + BN * ld + kBM * (BN + 4)) * sizeof(float);
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(nce_partial_f32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = true; }
+        nce_partial_f32_kernel<BN><<<grid, kSimtThreads, smem, st>>>(q, queue, (int)B, (int)D, K, inv_T, n_splits, pm, pl, pmm, pO);
+    }
+    MOMA_CUDA_LAUNCH_CHECK("nce_partial(f32)");
+    return MOMA_OK;
+}
+
+}  // namespace moma
+
+using namespace moma;
+
+extern "C" __attribute__((visibility("default"))) int moma_nce_num_splits(int64_t B, int64_t D, int64_t K_local, int dtype) {
+    if (B <= 0 || D <= 0 || K_local <= 0) return 1;
+    if (dtype == MOMA_BF16 && nce_tc_supported(B, D, K_local)) return nce_tc_num_splits(B, D, K_local);
+    // fp32 SIMT: aim for ~2 CTAs per SM, at least 4 tiles of work per split
+    const int64_t mt = (B + kBM - 1) / kBM;
+    const int64_t bn = D <= 256 ? 64 : 32;
+    const int64_t tiles = (K_local + bn - 1) / bn;
+    int64_t s = (2 * (int64_t)sm_count() + mt - 1) / mt;
+    if (s > tiles / 4) s = tiles / 4;
+    if (s < 1) s = 1;
+    if (s > 1024) s = 1024;
+    return (int)s;
+}
+
+extern "C" __attribute__((visibility("default"))) int moma_nce_partial(const void* q, const void* queue, int64_t B, int64_t D,
+                                int64_t K_local, float inv_T, int dtype, int n_splits,
+                                float* part_m, float* part_l, float* part_mmax, float* part_O,
+                                moma_stream_t stream) {
+    MOMA_REQUIRE(B > 0 && D > 0 && K_local > 0 && n_splits > 0, MOMA_ERR_INVALID,
+                 "nce_partial: bad shape B=%lld D=%lld K=%lld splits=%d", (long long)B, (long long)D,
+                 (long long)K_local, n_splits);
+    MOMA_REQUIRE(q && queue && part_m && part_l && part_mmax && part_O, MOMA_ERR_INVALID, "nce_partial: null pointer");
+    MOMA_REQUIRE(aligned16(q) && aligned16(queue) && aligned16(part_O), MOMA_ERR_ALIGN, "nce_partial: unaligned pointer");
+    MOMA_REQUIRE(B < (1ll << 30) && K_local < (1ll << 40), MOMA_ERR_UNSUPPORTED, "nce_partial: shape too large");
+    if (dtype == MOMA_F32)
+        return partial_f32(static_cast<const float*>(q), static_cast<const float*>(queue), B, D, K_local,
+                           inv_T, n_splits, part_m, part_l, part_mmax, part_O, as_stream(stream));
+    MOMA_REQUIRE(dtype == MOMA_BF16, MOMA_ERR_INVALID, "nce_partial: unknown dtype %d", dtype);
+    MOMA_REQUIRE(nce_tc_supported(B, D, K_local), MOMA_ERR_UNSUPPORTED,
+                 "nce_partial(bf16): D=%lld unsupported by the tcgen05 kernel (need D in {64,128,256})",
+                 (long long)D);
+    return nce_tc_partial(q, queue, B, D, K_local, inv_T, n_splits, part_m, part_l, part_mmax, part_O,
+                          as_stream(stream));
+}
+
+extern "C" __attribute__((visibility("default"))) int moma_nce_combine(const float* part_m, const float* part_l, const float* part_mmax,
+                                const float* part_O, int n_parts, const float* q_f32,
+                                const float* kpos_f32, int64_t B, int64_t D, float inv_T,
+                                float* loss_rows, float* dq_unit, int32_t* pos_is_max,
+                                float* max_logit, moma_stream_t stream) {
+    MOMA_REQUIRE(B > 0 && D > 0 && n_parts > 0, MOMA_ERR_INVALID, "nce_combine: bad shape");
+    MOMA_REQUIRE(part_m && part_l && part_mmax && part_O && q_f32 && kpos_f32 && loss_rows && dq_unit && pos_is_max,
+                 MOMA_ERR_INVALID, "nce_combine: null pointer");
+    nce_combine_kernel<<<(unsigned)B, 128, 0, as_stream(stream)>>>(
+        part_m, part_l, part_mmax, part_O, n_parts, q_f32, kpos_f32, (int)B, (int)D, inv_T,
+        loss_rows, dq_unit, pos_is_max, max_logit);
+    MOMA_CUDA_LAUNCH_CHECK("nce_combine");
+    return MOMA_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int moma_nce_logits(const void* q, const void* kpos, const void* queue, int64_t B,
+                               int64_t D, int64_t K, float T, int dtype, float* logits,
+                               moma_stream_t stream) {
+    MOMA_REQUIRE(B > 0 && D > 0 && K > 0 && q && kpos && queue && logits, MOMA_ERR_INVALID, "nce_logits: bad arguments");
+    MOMA_REQUIRE(T != 0.f, MOMA_ERR_INVALID, "nce_logits: T == 0");
+    const dim3 grid((unsigned)((K + 63) / 64), (unsigned)((B + 63) / 64));
+    cudaStream_t st = as_stream(stream);
+    if (dtype == MOMA_F32) {
+        nce_logits_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(q), static_cast<const float*>(queue), (int)B, (int)D, K, T, logits);
+        nce_pos_kernel<float><<<(unsigned)((B + 3) / 4), 128, 0, st>>>(static_cast<const float*>(q), static_cast<const float*>(kpos), (int)B, (int)D, T, logits, K + 1);
+    } else if (dtype == MOMA_BF16) {
+        using bf = __nv_bfloat16;
+        nce_logits_kernel<bf><<<grid, 256, 0, st>>>(static_cast<const bf*>(q), static_cast<const bf*>(queue), (int)B, (int)D, K, T, logits);
+        nce_pos_kernel<bf><<<(unsigned)((B + 3) / 4), 128, 0, st>>>(static_cast<const bf*>(q), static_cast<const bf*>(kpos), (int)B, (int)D, T, logits, K + 1);
+    } else {
+        return fail(MOMA_ERR_INVALID, "nce_logits: unknown dtype %d", dtype);
+    }
+    MOMA_CUDA_LAUNCH_CHECK("nce_logits");
+    return MOMA_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int moma_nce_logits_qk(const float* q, const float* kpos, int64_t B, int64_t D, float T,
+                                  float* out, moma_stream_t stream) {
+    MOMA_REQUIRE(B > 0 && D > 0 && q && kpos && out && T != 0.f, MOMA_ERR_INVALID, "nce_logits_qk: bad arguments");
+    nce_pos_kernel<float><<<(unsigned)((B + 3) / 4), 128, 0, as_stream(stream)>>>(q, kpos, (int)B, (int)D, T, out, 1);
+    MOMA_CUDA_LAUNCH_CHECK("nce_logits_qk");
+    return MOMA_OK;
+}

@@ -1,0 +1,599 @@
+// InfoNCE logits + cross-entropy forward/backward, BF16 tensor-core path for sm_100a.
+//
+// One flash-style pass over the (bf16 shadow of the) queue per query tile:
+//     S = Q . Tile^T        tcgen05.mma  (A = Q smem, B = queue tile smem, both K-major)  -> TMEM
+//     P = exp2(S*c - m)     softmax warps: tcgen05.ld -> registers -> bf16 -> tcgen05.st   -> TMEM
+//     O += P . Tile         tcgen05.mma  (A = P from TMEM, B = the SAME smem tile, MN-major) -> TMEM
+// so the [B, K] logits never leave the SM and the queue tile is fetched once (TMA, 128B swizzle)
+// for both contractions.  The running (m, l, O) per row are written as per-split partials and
+// merged (splits x shards, + positive column) by moma_nce_combine in nce_simt.cu.
+//
+// Replaces MoMA/mem_moco.py:29-49, learning/contrast_trainer.py:189-205 and their backward.
+//
+// CTA layout (warp-specialised, 1 CTA / SM):
+//   warp 0      TMA producer (Q once, queue tiles through a 4-stage mbarrier ring)
+//   warp 1      MMA issuer (one elected lane issues every tcgen05.mma / tcgen05.commit)
+//   warp 2      TMEM allocator (512 columns)
+//   warps 4-7   softmax group 0, warps 8-11 softmax group 1 (one thread per query row)
+// Two schedules share the code (template NQ):
+//   NQ = 2 (D <= 128, B > 128): two 128-row query tiles per CTA ping-pong, so the tensor pipe
+//           works on tile B while the softmax group of tile A is busy (TMEM: S0 S1 O0 O1).
+//   NQ = 1 (D = 256 or B <= 128): one query tile, S double-buffered, one softmax group.
+// Online softmax uses a lazily updated reference max (rescale O only when the row max grows
+// by more than 2^8), and tracks the true max separately for the top-1 flag.
+#include <cuda.h>
+#include <math_constants.h>
+#include <mutex>
+#include <unordered_map>
+#include "common.cuh"
+
+namespace moma {
+namespace tc {
+
+constexpr int kBM = 128;          // query rows per M-tile (UMMA M)
+constexpr int kStages = 4;        // queue-tile ring depth
+constexpr int kTmemCols = 512;
+constexpr float kLazyTau = 8.0f;  // log2 units
+
+__device__ int g_tc_error = 0;
+
+// ----------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU -- record a code and trap instead.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int code) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) {
+            atomicExch(&g_tc_error, code);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+
+#define TMEM_LD32(a, r)                                                                                  \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                               \
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"                                \
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"              \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),   \
+                   "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),            \
+                   "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),         \
+                   "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),         \
+                   "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),         \
+                   "=r"(r[31])                                                                           \
+                 : "r"(a) : "memory")
+
+#define TMEM_ST32(a, r)                                                                                  \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                         \
+                 "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"                               \
+                 "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"                     \
+                 ::"r"(a), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),  \
+                   "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]),      \
+                   "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),   \
+                   "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),   \
+                   "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory")
+
+#define TMEM_ST16(a, r)                                                                                  \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "                                         \
+                 "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"                              \
+                 ::"r"(a), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),  \
+                   "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]),      \
+                   "r"(r[14]), "r"(r[15]) : "memory")
+
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);      // .x (low 16 bits) = lo
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// UMMA shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2 (SW128)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): bf16 x bf16 -> f32
+//   [4,6) c_format=1 (F32) | [7,10) a_format=1 (BF16) | [10,13) b_format=1 | bit15 a_major | bit16 b_major
+//   [17,23) N>>3 | [24,29) M>>4
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct __align__(8) Bars {
+    uint64_t q_full;
+    uint64_t kv_full[kStages];
+    uint64_t kv_empty[kStages];
+    uint64_t s_full[2];
+    uint64_t p_full[2];
+    uint64_t pv_done[2];
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+
+template <int D, int NQ, int BN>
+struct Cfg {
+    static constexpr int KB = D / 64;                   // 64-column (128-byte) blocks per row
+    static constexpr int Q_BLOCK = kBM * 128;           // bytes of one 64-col block of a Q tile
+    static constexpr int Q_TILE = KB * Q_BLOCK;
+    static constexpr int K_BLOCK = BN * 128;
+    static constexpr int K_TILE = KB * K_BLOCK;
+    static constexpr int SMEM_DATA = NQ * Q_TILE + kStages * K_TILE;
+    static constexpr int SMEM_TOTAL = SMEM_DATA + 1024 /*align slack*/ + (int)sizeof(Bars);
+    static constexpr int THREADS = 128 * (1 + NQ);
+    static constexpr int S_COL0 = 0, S_COL1 = 128, O_COL = 256;   // TMEM columns
+    static_assert(256 + NQ * D <= kTmemCols, "TMEM budget");
+    static_assert(SMEM_TOTAL <= 227 * 1024, "smem budget");
+};
+
+template <int D, int NQ, int BN>
+__global__ void __launch_bounds__(128 * (1 + NQ), 1)
+nce_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+              int B, long long K_local, float scale_log2, int n_splits, float* __restrict__ part_m,
+              float* __restrict__ part_l, float* __restrict__ part_mmax, float* __restrict__ part_O,
+              float* __restrict__ dbg_S) {
+    using C = Cfg<D, NQ, BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mg = blockIdx.x, split = blockIdx.y;
+    const int T_total = (int)((K_local + BN - 1) / BN);
+    const int t0 = (int)((long long)T_total * split / n_splits);
+    const int t1 = (int)((long long)T_total * (split + 1) / n_splits);
+    const int nt = t1 - t0;
+    const int row_base = mg * NQ * kBM;
+    const int nq_active = (NQ == 2 && row_base + kBM < B) ? 2 : 1;
+
+    if (nt <= 0) {      // empty split: neutral partials
+        if (warp >= 4) {
+            const int g = (warp - 4) >> 2;
+            const int row = row_base + g * kBM + ((warp & 3) << 5) + lane;
+            if (row < B) {
+                const long long o = (long long)split * B + row;
+                part_m[o] = -CUDART_INF_F; part_mmax[o] = -CUDART_INF_F; part_l[o] = 0.f;
+                for (int d = 0; d < D; ++d) part_O[o * D + d] = 0.f;
+            }
+        }
+        return;
+    }
+
+    // carve shared memory (SWIZZLE_128B tiles need 1024-byte alignment)
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t q_smem = base;
+    const uint32_t kv_smem = base + NQ * C::Q_TILE;
+    Bars* bars = reinterpret_cast<Bars*>(smem_raw + (base - raw) + C::SMEM_DATA);
+    const uint32_t b_q_full = smem_u32(&bars->q_full);
+    auto b_kv_full = [&](int s) { return smem_u32(&bars->kv_full[s]); };
+    auto b_kv_empty = [&](int s) { return smem_u32(&bars->kv_empty[s]); };
+    auto b_s_full = [&](int b) { return smem_u32(&bars->s_full[b]); };
+    auto b_p_full = [&](int b) { return smem_u32(&bars->p_full[b]); };
+    auto b_pv_done = [&](int g) { return smem_u32(&bars->pv_done[g]); };
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_k);
+        mbar_init(b_q_full, 1);
+        for (int s = 0; s < kStages; ++s) { mbar_init(b_kv_full(s), 1); mbar_init(b_kv_empty(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(b_s_full(b), 1); mbar_init(b_p_full(b), 128); mbar_init(b_pv_done(b), 1); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(smem_u32(&bars->tmem_base), kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+    auto s_colf = [&](int b) { return tmem + (uint32_t)(b * C::S_COL1); };
+
+    // register budget: the producer/issuer warpgroup gives registers to the softmax warpgroups,
+    // which hold a whole 128-wide score row per thread
+    if (warp < 4) {
+      // the producer / issuer warpgroup hands registers to the softmax warpgroups, which hold a whole
+      // 128-wide score row per thread
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+      if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            mbar_expect_tx(b_q_full, nq_active * C::Q_TILE);
+            for (int g = 0; g < nq_active; ++g)
+                for (int kb = 0; kb < C::KB; ++kb)
+                    tma_load_2d(q_smem + g * C::Q_TILE + kb * C::Q_BLOCK, &tmap_q, kb * 64, row_base + g * kBM, b_q_full);
+            for (int i = 0; i < nt; ++i) {
+                const int s = i % kStages;
+                mbar_wait(b_kv_empty(s), ((i / kStages) & 1) ^ 1, 101);
+                mbar_expect_tx(b_kv_full(s), C::K_TILE);
+                for (int kb = 0; kb < C::KB; ++kb)
+                    tma_load_2d(kv_smem + s * C::K_TILE + kb * C::K_BLOCK, &tmap_k, kb * 64, (t0 + i) * BN, b_kv_full(s));
+            }
+        }
+      } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc(kBM, BN, 0, 0);     // S = Q . Tile^T
+            constexpr uint32_t idesc_o = make_idesc(kBM, D, 0, 1);      // O += P . Tile (B MN-major)
+            // descriptors advance by adding (bytes >> 4) to the 14-bit start-address field
+            const uint64_t q_desc0 = make_desc(q_smem, 16, 1024);
+            const uint64_t k_desc0 = make_desc(kv_smem, 16, 1024);                 // K-major view (S)
+            const uint64_t v_desc0 = make_desc(kv_smem, C::K_BLOCK, 1024);         // MN-major view (PV)
+            auto issue_s = [&](int g_q, int b, int stage) {
+                const uint64_t da0 = q_desc0 + (uint64_t)((g_q * C::Q_TILE) >> 4);
+                const uint64_t db0 = k_desc0 + (uint64_t)((stage * C::K_TILE) >> 4);
+#pragma unroll 1
+                for (int ks = 0; ks < D / 16; ++ks) {
+                    // 64-column block (ks >> 2), then the 16-element k-step inside the 128-byte swizzle row
+                    const uint32_t qoff = (uint32_t)((ks >> 2) * C::Q_BLOCK + (ks & 3) * 32) >> 4;
+                    const uint32_t koff = (uint32_t)((ks >> 2) * C::K_BLOCK + (ks & 3) * 32) >> 4;
+                    umma_ss(s_colf(b), da0 + qoff, db0 + koff, idesc_s, ks > 0 ? 1u : 0u);
+                }
+                umma_commit(b_s_full(b));
+            };
+            auto issue_pv = [&](int g_o, int b, int stage, bool accumulate) {
+                const uint64_t db0 = v_desc0 + (uint64_t)((stage * C::K_TILE) >> 4);
+                const uint32_t d_tmem = tmem + C::O_COL + g_o * D;
+#pragma unroll 1
+                for (int ks = 0; ks < BN / 16; ++ks) {
+                    // 16 queue rows (= 2 swizzle atoms of 8 rows x 128 B) per k-step
+                    umma_ts(d_tmem, s_colf(b) + ks * 8, db0 + (uint64_t)(ks * (2048 >> 4)), idesc_o,
+                            (accumulate || ks > 0) ? 1u : 0u);
+                }
+                umma_commit(b_pv_done(g_o));
+            };
+            mbar_wait(b_q_full, 0, 102);
+            if (NQ == 2) {
+                mbar_wait(b_kv_full(0), 0, 103);
+                tc_fence_after();
+                for (int g = 0; g < nq_active; ++g) issue_s(g, g, 0);
+                for (int i = 0; i < nt; ++i) {
+                    const int st = i % kStages;
+                    for (int g = 0; g < nq_active; ++g) {
+                        mbar_wait(b_p_full(g), i & 1, 104);
+                        tc_fence_after();
+                        issue_pv(g, g, st, i > 0);
+                        if (g == nq_active - 1) umma_commit(b_kv_empty(st));
+                        if (i + 1 < nt) {
+                            const int sn = (i + 1) % kStages;
+                            if (g == 0) { mbar_wait(b_kv_full(sn), ((i + 1) / kStages) & 1, 105); tc_fence_after(); }
+                            issue_s(g, g, sn);
+                        }
+                    }
+                }
+            } else {
+                mbar_wait(b_kv_full(0), 0, 103);
+                tc_fence_after();
+                issue_s(0, 0, 0);
+                if (nt > 1) { mbar_wait(b_kv_full(1), 0, 106); tc_fence_after(); issue_s(0, 1, 1); }
+                for (int i = 0; i < nt; ++i) {
+                    const int st = i % kStages, b = i & 1;
+                    mbar_wait(b_p_full(b), (i >> 1) & 1, 104);
+                    tc_fence_after();
+                    issue_pv(0, b, st, i > 0);
+                    umma_commit(b_kv_empty(st));
+                    if (i + 2 < nt) {
+                        const int sn = (i + 2) % kStages;
+                        mbar_wait(b_kv_full(sn), ((i + 2) / kStages) & 1, 105);
+                        tc_fence_after();
+                        issue_s(0, b, sn);
+                    }
+                }
+            }
+        }
+      }
+    } else if ((warp - 4) / 4 < nq_active) {
+        // ===================================================== softmax groups
+        if (NQ == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        const int g = (warp - 4) >> 2;
+        const int wq = warp & 3;                                 // TMEM lane quarter of this warp
+        const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+        const int row = row_base + g * kBM + wq * 32 + lane;
+        const uint32_t o_addr = tmem + lane_off + C::O_COL + g * D;
+        float m_ref = -CUDART_INF_F, m_true = -CUDART_INF_F, l_run = 0.f;
+        const bool ragged_last = (K_local % BN) != 0;
+
+        for (int i = 0; i < nt; ++i) {
+            const int b = (NQ == 2) ? g : (i & 1);
+            const uint32_t ph = (NQ == 2) ? (i & 1) : ((i >> 1) & 1);
+            mbar_wait(b_s_full(b), ph, 201);
+            tc_fence_after();
+            uint32_t v[BN];
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t* vc = v + 32 * c;
+                TMEM_LD32(s_colf(b) + lane_off + 32 * c, vc);
+            }
+            tmem_wait_ld();
+            if (dbg_S != nullptr && i == 0 && split == 0 && row < B) {
+#pragma unroll
+                for (int j = 0; j < BN; ++j) dbg_S[(long long)row * BN + j] = __uint_as_float(v[j]);
+            }
+            if (ragged_last && (t0 + i) == T_total - 1) {
+                const int valid = (int)(K_local - (long long)(T_total - 1) * BN);
+#pragma unroll
+                for (int j = 0; j < BN; ++j)
+                    if (j >= valid) v[j] = __float_as_uint(-CUDART_INF_F);
+            }
+            float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F, mx2 = -CUDART_INF_F, mx3 = -CUDART_INF_F;
+#pragma unroll
+            for (int j = 0; j < BN; j += 4) {
+                mx0 = fmaxf(mx0, __uint_as_float(v[j]));     mx1 = fmaxf(mx1, __uint_as_float(v[j + 1]));
+                mx2 = fmaxf(mx2, __uint_as_float(v[j + 2])); mx3 = fmaxf(mx3, __uint_as_float(v[j + 3]));
+            }
+            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+            m_true = fmaxf(m_true, mx);
+            const bool need = mx > m_ref + kLazyTau;                 // always true on the first tile
+            if (i > 0 && __any_sync(0xffffffffu, need)) {
+                // rare: the running max grew by > 2^8 -> rescale O and l to the new reference
+                mbar_wait(b_pv_done(g), (i - 1) & 1, 202);
+                tc_fence_after();
+                const float f = need ? ex2(m_ref - mx) : 1.0f;
+#pragma unroll 1
+                for (int c = 0; c < D / 32; ++c) {
+                    uint32_t o[32];
+                    TMEM_LD32(o_addr + 32 * c, o);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * f);
+                    TMEM_ST32(o_addr + 32 * c, o);
+                }
+                tmem_wait_st();
+                l_run *= f;
+            }
+            if (need) m_ref = mx;
+            const float neg = -m_ref;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float p0 = ex2(fmaf(__uint_as_float(v[32 * c + j]), scale_log2, neg));
+                    const float p1 = ex2(fmaf(__uint_as_float(v[32 * c + j + 1]), scale_log2, neg));
+                    const float p2 = ex2(fmaf(__uint_as_float(v[32 * c + j + 2]), scale_log2, neg));
+                    const float p3 = ex2(fmaf(__uint_as_float(v[32 * c + j + 3]), scale_log2, neg));
+                    s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+                    pk[j >> 1] = pack_bf16(p0, p1);
+                    pk[(j >> 1) + 1] = pack_bf16(p2, p3);
+                }
+                TMEM_ST16(s_colf(b) + lane_off + 16 * c, pk);      // P aliases the S buffer (bf16 pairs)
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(b_p_full(b));
+            l_run += (s0 + s1) + (s2 + s3);
+        }
+
+        // epilogue: O (TMEM) -> part_O, stats
+        mbar_wait(b_pv_done(g), (nt - 1) & 1, 203);
+        tc_fence_after();
+        const long long orow = (long long)split * B + row;
+#pragma unroll 1
+        for (int c = 0; c < D / 32; ++c) {
+            uint32_t o[32];
+            TMEM_LD32(o_addr + 32 * c, o);
+            tmem_wait_ld();
+            if (row < B) {
+                float4* dst = reinterpret_cast<float4*>(part_O + orow * D + 32 * c);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    dst[j] = make_float4(__uint_as_float(o[4 * j]), __uint_as_float(o[4 * j + 1]),
+                                         __uint_as_float(o[4 * j + 2]), __uint_as_float(o[4 * j + 3]));
+            }
+        }
+        if (row < B) {
+            constexpr float kLn2 = 0.6931471805599453f;
+            part_m[orow] = m_ref * kLn2;
+            part_mmax[orow] = m_true * kLn2;
+            part_l[orow] = l_run;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem, kTmemCols);
+}
+
+// ----------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// [rows, D] bf16 row-major, box = 64 columns (128 B) x box_rows rows, 128-byte swizzle, zero OOB fill
+static int make_map(CUtensorMap* out, const void* ptr, long long rows, int D, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    MOMA_REQUIRE(fn != nullptr, MOMA_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (driver too old?)");
+    const cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)D * 2};
+    const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MOMA_REQUIRE(r == CUDA_SUCCESS, MOMA_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return MOMA_OK;
+}
+
+struct MapKey {
+    const void* p; long long rows; int D; int box;
+    bool operator==(const MapKey& o) const { return p == o.p && rows == o.rows && D == o.D && box == o.box; }
+};
+struct MapHash {
+    size_t operator()(const MapKey& k) const {
+        return std::hash<const void*>()(k.p) ^ (std::hash<long long>()(k.rows) * 31) ^ (size_t)(k.D * 131 + k.box);
+    }
+};
+// descriptor cache (the only retained state: keyed by pointer/shape, no device memory held)
+static int cached_map(CUtensorMap* out, const void* ptr, long long rows, int D, int box_rows) {
+    static std::mutex mu;
+    static std::unordered_map<MapKey, CUtensorMap, MapHash> cache;
+    const MapKey key{ptr, rows, D, box_rows};
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return MOMA_OK; }
+    int rc = make_map(out, ptr, rows, D, box_rows);
+    if (rc != MOMA_OK) return rc;
+    if (cache.size() > 256) cache.clear();
+    cache.emplace(key, *out);
+    return MOMA_OK;
+}
+
+static void pick(int64_t B, int64_t D, int* nq, int* bn) {
+    *nq = (D == 256 || B <= kBM) ? 1 : 2;
+    *bn = (D == 256) ? 64 : 128;
+}
+
+template <int D, int NQ, int BN>
+static int launch(const void* q, const void* queue, int64_t B, int64_t K_local, float inv_T, int n_splits,
+                  float* pm, float* pl, float* pmm, float* pO, float* dbg, cudaStream_t st) {
+    using C = Cfg<D, NQ, BN>;
+    CUtensorMap mq, mk;
+    int rc = cached_map(&mq, q, B, D, kBM);
+    if (rc != MOMA_OK) return rc;
+    rc = cached_map(&mk, queue, K_local, D, BN);
+    if (rc != MOMA_OK) return rc;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(nce_tc_kernel<D, NQ, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_TOTAL);
+        MOMA_REQUIRE(e == cudaSuccess, MOMA_ERR_CUDA, "nce_tc: smem attribute: %s", cudaGetErrorString(e));
+        attr = true;
+    }
+    const dim3 grid((unsigned)((B + NQ * kBM - 1) / (NQ * kBM)), (unsigned)n_splits);
+    const float scale_log2 = inv_T * 1.4426950408889634f;
+    nce_tc_kernel<D, NQ, BN><<<grid, C::THREADS, C::SMEM_TOTAL, st>>>(mq, mk, (int)B, (long long)K_local, scale_log2,
+                                                                     n_splits, pm, pl, pmm, pO, dbg);
+    MOMA_CUDA_LAUNCH_CHECK("nce_partial(bf16/tcgen05)");
+    return MOMA_OK;
+}
+
+static int dispatch(const void* q, const void* queue, int64_t B, int64_t D, int64_t K_local, float inv_T,
+                    int n_splits, float* pm, float* pl, float* pmm, float* pO, float* dbg, cudaStream_t st) {
+    MOMA_REQUIRE(inv_T > 0.f, MOMA_ERR_INVALID, "nce_tc: temperature must be positive");
+    MOMA_REQUIRE((reinterpret_cast<uintptr_t>(q) & 127) == 0 && (reinterpret_cast<uintptr_t>(queue) & 127) == 0,
+                 MOMA_ERR_ALIGN, "nce_tc: q / queue must be 128-byte aligned for TMA");
+    int nq, bn;
+    pick(B, D, &nq, &bn);
+    if (D == 64) return nq == 2 ? launch<64, 2, 128>(q, queue, B, K_local, inv_T, n_splits, pm, pl, pmm, pO, dbg, st)
+                                : launch<64, 1, 128>(q, queue, B, K_local, inv_T, n_splits, pm, pl, pmm, pO, dbg, st);
+    if (D == 128) return nq == 2 ? launch<128, 2, 128>(q, queue, B, K_local, inv_T, n_splits, pm, pl, pmm, pO, dbg, st)
+                                 : launch<128, 1, 128>(q, queue, B, K_local, inv_T, n_splits, pm, pl, pmm, pO, dbg, st);
+    if (D == 256) return launch<256, 1, 64>(q, queue, B, K_local, inv_T, n_splits, pm, pl, pmm, pO, dbg, st);
+    return fail(MOMA_ERR_UNSUPPORTED, "nce_tc: D=%lld unsupported", (long long)D);
+}
+
+}  // namespace tc
+
+bool nce_tc_supported(int64_t B, int64_t D, int64_t K_local) {
+    return (D == 64 || D == 128 || D == 256) && B > 0 && K_local > 0 && B < (1ll << 30) && K_local < (1ll << 36);
+}
+
+int nce_tc_num_splits(int64_t B, int64_t D, int64_t K_local) {
+    int nq, bn;
+    tc::pick(B, D, &nq, &bn);
+    const int64_t mgroups = (B + nq * tc::kBM - 1) / (nq * tc::kBM);
+    const int64_t tiles = (K_local + bn - 1) / bn;
+    int64_t s = sm_count() / mgroups;
+    if (s > tiles) s = tiles;
+    if (s < 1) s = 1;
+    return (int)s;
+}
+
+int nce_tc_partial(const void* q, const void* queue, int64_t B, int64_t D, int64_t K_local, float inv_T,
+                   int n_splits, float* part_m, float* part_l, float* part_mmax, float* part_O,
+                   cudaStream_t stream) {
+    return tc::dispatch(q, queue, B, D, K_local, inv_T, n_splits, part_m, part_l, part_mmax, part_O, nullptr, stream);
+}
+
+}  // namespace moma
+
+using namespace moma;
+
+// Debug / test entry points (declared in include/moma_b200.h under "debug").
+extern "C" __attribute__((visibility("default"))) int moma_debug_nce_tc(
+    const void* q, const void* queue, int64_t B, int64_t D, int64_t K_local, float inv_T, int n_splits,
+    float* part_m, float* part_l, float* part_mmax, float* part_O, float* dbg_S, moma_stream_t stream) {
+    MOMA_REQUIRE(nce_tc_supported(B, D, K_local), MOMA_ERR_UNSUPPORTED, "debug_nce_tc: unsupported shape");
+    return tc::dispatch(q, queue, B, D, K_local, inv_T, n_splits, part_m, part_l, part_mmax, part_O, dbg_S,
+                        as_stream(stream));
+}
+
+// Synchronising read of the device-side protocol-error flag (0 = none).
+extern "C" __attribute__((visibility("default"))) int moma_debug_tc_error(void) {
+    int v = 0;
+    if (cudaMemcpyFromSymbol(&v, tc::g_tc_error, sizeof(int)) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return v;
+}

@@ -1,0 +1,305 @@
+"""Momentum memory bank -- host-side mirror of the reference MoMA/mem_moco.py.
+
+Same classes, constructor signatures, buffers (``memory`` / ``memory_s`` /
+``memory_t``, fp32 ``[K, D]`` in ``state_dict``) and the ``index`` attribute, so
+helper/loops_moma.py:331 and train_student_moma.py:333-336 use it unchanged.
+The arithmetic is done by the sm_100a kernels behind include/moma_b200.h:
+
+  * logits + CrossEntropy + d loss/d q : one fused pass (``ops.nce_rows``); the
+    ``[B, K+1]`` logits are returned as a :class:`LazyLogits` handle and never
+    written to HBM (reference: mem_moco.py:29-49 + contrast_trainer.py:189-205);
+  * the per-step ``memory.clone()`` (mem_moco.py:89) is eliminated: kernels are
+    stream-ordered, the loss pass reads the queue before the enqueue overwrites it;
+  * ring enqueue + pointer (mem_moco.py:14-27): ``ops.enqueue`` (ids computed
+    in-kernel, fp32 master + bf16 shadow written together).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .lazy_logits import LazyLogits
+
+
+class BaseMoCo(nn.Module):
+    """base class for MoCo-style memory cache (reference mem_moco.py:6-66)"""
+
+    def __init__(self, K=65536, T=0.07):
+        super().__init__()
+        self.K = K
+        self.T = T
+        self.index = 0
+        self._shadows = {}          # buffer name -> (bf16 shadow, data_ptr, version) ; non-persistent
+        self._zero_labels = {}
+
+    # ---- pointer / enqueue ------------------------------------------------
+    def _update_pointer(self, bsz):
+        # mem_moco.py:14-15
+        self.index = (self.index + bsz) % self.K
+
+    def _shadow_of(self, queue: torch.Tensor, create: bool = True):
+        """bf16 shadow of a queue buffer, rebuilt when the fp32 master was replaced or
+        modified behind our back (``.cuda()``, ``load_state_dict``, ``broadcast_memory``)."""
+        if not queue.is_cuda or queue.shape[1] % 8 != 0:
+            return None
+        for name, (sh, ptr, ver) in list(self._shadows.items()):
+            if ptr == queue.data_ptr():
+                if ver != queue._version or sh.device != queue.device:
+                    ops.cast_bf16(queue, sh)
+                    self._shadows[name] = (sh, ptr, queue._version)
+                return sh
+        if not create:
+            return None
+        sh = torch.empty(queue.shape, dtype=torch.bfloat16, device=queue.device)
+        ops.cast_bf16(queue, sh)
+        if len(self._shadows) > 4:
+            self._shadows.clear()
+        self._shadows[f"s{len(self._shadows)}"] = (sh, queue.data_ptr(), queue._version)
+        return sh
+
+    def _update_memory(self, k, queue):
+        """queue[(index + j) % K] = k[j]   (mem_moco.py:17-27)"""
+        with torch.no_grad():
+            if k.shape[0] > self.K:
+                raise RuntimeError(f"enqueue of {k.shape[0]} rows into a queue of K={self.K}: duplicate ids "
+                                   "(undefined in the reference, mem_moco.py:24-27)")
+            shadow = self._shadow_of(queue, create=ops.get_precision() == "bf16")
+            ops.enqueue(k, queue, shadow, self.K, self.index)
+
+    # ---- logits -----------------------------------------------------------
+    def _compute_logit(self, q, k, queue):
+        """Dense logits (mem_moco.py:29-49); used by the variants' fallbacks and tests."""
+        out = ops.nce_logits(q, k, queue, self.T)
+        return out.squeeze().contiguous()
+
+    def _compute_logit_qk(self, q, k):
+        """mem_moco.py:51-66"""
+        return ops.nce_logits_qk(q, k, self.T).squeeze().contiguous()
+
+    def _labels(self, bsz, device):
+        key = (bsz, str(device))
+        lab = self._zero_labels.get(key)
+        if lab is None:
+            lab = self._zero_labels[key] = torch.zeros(bsz, dtype=torch.long, device=device)
+        return lab
+
+    def _fused_logits(self, q, k, queue, labels):
+        """Fused loss pass over `queue`; returns the lazy handle standing in for
+        ``_compute_logit(q, k, queue.clone())``."""
+        bsz, D = q.shape
+        K = queue.shape[0]
+        if not ops.fused_nce_supported(D):
+            return self._compute_logit(q, k, queue)          # dense escape hatch (e.g. D = 1280, 2048)
+        precision = ops.get_precision()
+        shadow = self._shadow_of(queue) if precision == "bf16" and ops.bf16_supported(D) else None
+        rows, pim, mx = ops.nce_rows(q, k, queue, shadow, self.T, precision)
+        T = self.T
+        # rows about to be overwritten by this step's enqueue: keep them so a late
+        # materialisation still sees the pre-enqueue queue (the reference's clone, :89)
+        state = {"index": self.index, "saved": None}
+        q_d, k_d = q.detach(), k.detach()
+
+        def max_logit():
+            return mx
+
+        def materialize():
+            src = shadow if shadow is not None else queue
+            dense = ops.nce_logits(q, k_d, src, T)
+            if state["saved"] is not None:
+                ids, old = state["saved"]
+                patch = ops.nce_logits(q, k_d, old, T)[:, 1:]
+                dense = dense.index_copy(1, ids + 1, patch)
+            return dense.squeeze().contiguous()
+
+        shape = (bsz, K + 1) if bsz != 1 else (K + 1,)
+        handle = LazyLogits(shape, q.device, rows, pim, max_logit, labels, materialize)
+        handle._enqueue_state = state
+        return handle
+
+    def _remember_overwritten(self, handles, queue, n):
+        """Save the n queue rows the coming enqueue overwrites (n x D, tiny) for late materialisation."""
+        live = [h for h in handles if isinstance(h, LazyLogits)]
+        if not live or n == 0:
+            return
+        ids = ops.enqueue_ids(n, self.index, self.K, queue.device)
+        src = self._shadow_of(queue, create=False)
+        old = (src if (src is not None and ops.get_precision() == "bf16") else queue).index_select(0, ids)
+        for h in live:
+            h._enqueue_state["saved"] = (ids, old)
+
+
+class MoCo(BaseMoCo):
+    """Single Modal (e.g., RGB) MoCo-style cache (reference mem_moco.py:69-100)"""
+
+    def __init__(self, n_dim, K=65536, T=0.07, mem_name='memory'):
+        super().__init__(K, T)
+        # same RNG draw as the reference: K*n_dim normals from the global CPU generator, then L2 rows
+        self.register_buffer(mem_name, torch.randn(K, n_dim))
+        self.memory = F.normalize(self.memory)
+        self.track_overwritten = False      # set True to allow materialising logits after the enqueue
+
+    def forward(self, q, k, all_k=None):
+        """
+        Args:
+          q: query on current node
+          k: key on current node
+          all_k: gather of feats across nodes; otherwise use k
+        Returns (logits, labels) as mem_moco.py:77-100.
+        """
+        bsz = q.size(0)
+        k = k.detach()
+        labels = self._labels(bsz, q.device)
+        logits = self._fused_logits(q, k, self.memory, labels)
+        all_k = all_k if all_k is not None else k
+        if self.track_overwritten:
+            self._remember_overwritten([logits], self.memory, all_k.size(0))
+        elif isinstance(logits, LazyLogits):
+            logits._materialize = _stale_after_enqueue
+        self._update_memory(all_k, self.memory)
+        self._update_pointer(all_k.size(0))
+        return logits, labels
+
+
+def _stale_after_enqueue():
+    raise RuntimeError(
+        "LazyLogits: the dense [B, K+1] logits were requested after the queue was updated. Only "
+        "CrossEntropyLoss (zero labels) and top-1 accuracy are served without materialising; set "
+        "`contrast.track_overwritten = True` (or MOMA_B200_LOGITS=dense) to allow other uses.")
+
+
+class MoCoAtt(BaseMoCo):
+    """MoCo cache with attention applied inside the memory (reference mem_moco.py:103-161)"""
+
+    def __init__(self, n_dim, K=65536, T=0.07, mem_name='memory'):
+        super().__init__(K, T)
+        self.register_buffer(mem_name, torch.randn(K, n_dim))
+        self.memory = F.normalize(self.memory)
+
+    def forward(self, q, k, all_k=None, attn=None, criterion_kd=None):
+        bsz = q.size(0)
+        k = k.detach()
+        # the attended queue is a new tensor every step (no clone needed for the untouched case:
+        # the loss pass below is stream-ordered before the enqueue)
+        queue = self.memory.detach()
+        if attn == 'all':
+            out = criterion_kd.atts(torch.cat([q, k, queue], dim=0))
+            q, k, queue = out[:bsz], out[bsz:2 * bsz], out[2 * bsz:]
+        elif attn == 'qk':
+            out = criterion_kd.atts(torch.cat([q, k], dim=0))
+            q, k = out[:bsz], out[bsz:]
+        elif attn == 'dual':
+            out_p = criterion_kd.atts_p(torch.cat([q, queue], dim=0))
+            q, queue = out_p[:bsz], out_p[bsz:]
+            out_n = criterion_kd.atts_n(torch.cat([k, queue], dim=0))
+            k, queue = out_n[:bsz], out_n[bsz:]
+        elif attn == 'dual2':
+            out_p = criterion_kd.atts_p(torch.cat([q, k], dim=0))
+            q = out_p[:bsz]
+            out_n = criterion_kd.atts_n(torch.cat([k, q], dim=0))
+            k = out_n[:bsz]
+        elif attn in ['self_qk', 'self_qkv2']:
+            q = criterion_kd.atts_q(q)
+            k = criterion_kd.atts_k(k)
+        else:
+            q = criterion_kd.atts_q(q)
+            k = criterion_kd.atts_k(k)
+            queue = criterion_kd.atts_queue(queue)
+
+        labels = self._labels(bsz, q.device)
+        if attn == 'dual2':
+            logits = self._compute_logit_qk(q, k)
+        elif torch.is_grad_enabled() and (k.requires_grad or queue.requires_grad):
+            # the attended k / queue carry gradients into the attention parameters (the reference
+            # only detaches k *before* the attention, :116): keep full autograd on the dense form
+            logits = _dense_logits_autograd(q, k, queue, self.T)
+        else:
+            logits = self._fused_logits(q, k, queue.contiguous(), labels)
+
+        all_k = all_k if all_k is not None else k
+        if isinstance(logits, LazyLogits):
+            logits._materialize = _stale_after_enqueue
+        self._update_memory(all_k, self.memory)
+        self._update_pointer(all_k.size(0))
+        return logits, labels
+
+
+def _dense_logits_autograd(q, k, queue, T):
+    """Reference formulation with full autograd (k / queue may carry gradients in the
+    MoCoAtt concat modes, where the reference does not detach the attended tensors)."""
+    bsz = q.shape[0]
+    pos = (q * k).sum(1, keepdim=True)
+    neg = q @ queue.t()
+    return (torch.cat((pos, neg), dim=1) / T).squeeze().contiguous()
+
+
+class _DualQueue(BaseMoCo):
+    def __init__(self, n_dim, K=65536, T=0.07):
+        super().__init__(K, T)
+        self.register_buffer('memory_s', torch.randn(K, n_dim))
+        self.register_buffer('memory_t', torch.randn(K, n_dim))
+        self.memory_s = F.normalize(self.memory_s)
+        self.memory_t = F.normalize(self.memory_t)
+
+    def _finish(self, handles, k, k_t, all_k, all_k_t):
+        all_k = all_k if all_k is not None else k
+        all_k_t = all_k_t if all_k_t is not None else k_t
+        for h in handles:
+            if isinstance(h, LazyLogits):
+                h._materialize = _stale_after_enqueue
+        self._update_memory(all_k, self.memory_s)
+        self._update_memory(all_k_t, self.memory_t)
+        self._update_pointer(all_k.size(0))
+
+
+class MoCoST(_DualQueue):
+    """Two queues, student->student and student->teacher logits (reference mem_moco.py:165-204)"""
+
+    def forward(self, q, k, k_t, all_k=None, all_k_t=None):
+        bsz = q.size(0)
+        k = k.detach()
+        k_t = k_t.detach()
+        labels = self._labels(bsz, q.device)
+        logits_ss = self._fused_logits(q, k, self.memory_s, labels)
+        logits_st = self._fused_logits(q, k_t, self.memory_t, labels)
+        self._finish([logits_ss, logits_st], k, k_t, all_k, all_k_t)
+        return logits_ss, logits_st, labels
+
+
+class MoCoSSTT(_DualQueue):
+    """Two queues, up to four logits sharing one pointer (reference mem_moco.py:208-253)"""
+
+    def forward(self, q, k, q_t=None, k_t=None, all_k=None, all_k_t=None):
+        bsz = q.size(0)
+        k = k.detach()
+        k_t = k_t.detach()
+        labels = self._labels(bsz, q.device)
+        logits_ss = self._fused_logits(q, k, self.memory_s, labels)
+        logits_st = self._fused_logits(q, k_t, self.memory_t, labels)
+        outs = [logits_ss, logits_st]
+        if q_t is not None:
+            outs.append(self._fused_logits(q_t, k, self.memory_s, labels))
+            outs.append(self._fused_logits(q_t, k_t, self.memory_t, labels))
+        self._finish(outs, k, k_t, all_k, all_k_t)
+        return (*outs, labels)
+
+
+def build_mem(opt):
+    """Factory on opt.mem (reference mem_moco.py:256-273).  With ``opt.shard_queue`` (or
+    MOMA_B200_SHARD_QUEUE=1) and an initialised process group of world size > 1, MoCo is
+    built with its queue sharded by K across ranks (moma_b200.sharded.ShardedMoCo)."""
+    import os
+    if opt.mem == 'MoCoSSTT':
+        return MoCoSSTT(opt.feat_dim, opt.nce_k, opt.nce_t)
+    if opt.mem == 'MoCoST':
+        return MoCoST(opt.feat_dim, opt.nce_k, opt.nce_t)
+    if opt.mem == 'MoCoAtt':
+        return MoCoAtt(opt.feat_dim, opt.nce_k, opt.nce_t)
+    want_shard = bool(getattr(opt, "shard_queue", False)) or os.environ.get("MOMA_B200_SHARD_QUEUE") == "1"
+    if want_shard:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            from .sharded import ShardedMoCo
+            return ShardedMoCo(opt.feat_dim, opt.nce_k, opt.nce_t)
+    return MoCo(opt.feat_dim, opt.nce_k, opt.nce_t)

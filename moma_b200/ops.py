@@ -1,0 +1,344 @@
+"""torch-facing wrappers over the C ABI (include/moma_b200.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every arithmetic op
+of the hot path is a kernel in libmoma_b200.so, called with raw pointers on the
+current CUDA stream.  There is no CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, check
+
+_PRECISION = os.environ.get("MOMA_B200_PRECISION", "bf16").lower()
+
+
+def set_precision(mode: str) -> None:
+    """'bf16' (default; tcgen05 tensor-core InfoNCE, 1e-3 parity) or 'fp32' (SIMT, 1e-5 parity)."""
+    global _PRECISION
+    mode = mode.lower()
+    if mode not in ("bf16", "fp32"):
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+    _PRECISION = mode
+
+
+def get_precision() -> str:
+    return _PRECISION
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts: torch.Tensor) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("moma_b200: expected CUDA tensors (there is no CPU fallback); got a "
+                               f"{t.device} tensor")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ----------------------------------------------------------------------------- EMA
+class EmaPlan:
+    """Chunk table for one (model, model_ema) parameter list (built once, reused)."""
+
+    def __init__(self, srcs: Sequence[torch.Tensor], dsts: Sequence[torch.Tensor]):
+        lib = _lib.load()
+        n = len(srcs)
+        self.key = plan_key(srcs, dsts)
+        numels = (ctypes.c_int64 * n)(*[int(d.numel()) for d in dsts])
+        n_chunks, nbytes = ctypes.c_int64(0), ctypes.c_size_t(0)
+        check(lib.moma_ema_plan_size(n, numels, ctypes.byref(n_chunks), ctypes.byref(nbytes)))
+        self.n_chunks = n_chunks.value
+        self.elements = sum(int(d.numel()) for d in dsts)
+        host = torch.empty(max(nbytes.value, 32), dtype=torch.uint8).pin_memory() if torch.cuda.is_available() \
+            else torch.empty(max(nbytes.value, 32), dtype=torch.uint8)
+        sp = (ctypes.c_void_p * n)(*[s.data_ptr() for s in srcs])
+        dp = (ctypes.c_void_p * n)(*[d.data_ptr() for d in dsts])
+        check(lib.moma_ema_plan_fill(n, sp, dp, numels, host.data_ptr(), host.numel()))
+        self.host_table = host
+        self.table = host.to(dsts[0].device, non_blocking=False) if n else host
+
+    def run(self, m: float) -> None:
+        check(_lib.load().moma_ema_multi(_p(self.table), self.n_chunks, float(m), float(1 - m), _stream()))
+
+
+def plan_key(srcs, dsts) -> Tuple:
+    return tuple((s.data_ptr(), d.data_ptr(), d.numel()) for s, d in zip(srcs, dsts))
+
+
+_EMA_PLANS = {}
+
+
+def ema_update(srcs: Sequence[torch.Tensor], dsts: Sequence[torch.Tensor], m: float) -> None:
+    """dst = dst*m + (1-m)*src for every pair, one launch.  Mirrors the error
+    behaviour of learning/contrast_trainer.py:207-211 (shape mismatch raises)."""
+    srcs, dsts = list(srcs), list(dsts)
+    n = min(len(srcs), len(dsts))                      # zip() semantics of the reference
+    srcs, dsts = srcs[:n], dsts[:n]
+    if n == 0:
+        return
+    for s, d in zip(srcs, dsts):
+        if s.shape != d.shape:
+            raise RuntimeError(f"The size of tensor a {tuple(d.shape)} must match the size of tensor b "
+                               f"{tuple(s.shape)} (momentum_update)")
+        if s.dtype != torch.float32 or d.dtype != torch.float32:
+            raise RuntimeError("moma_b200.ema_update: only float32 parameters are supported")
+        if not (s.is_contiguous() and d.is_contiguous()):
+            raise RuntimeError("moma_b200.ema_update: parameters must be contiguous")
+    _need_cuda(*srcs, *dsts)
+    key = plan_key(srcs, dsts)
+    plan = _EMA_PLANS.get(key)
+    if plan is None:
+        if len(_EMA_PLANS) > 64:
+            _EMA_PLANS.clear()
+        plan = _EMA_PLANS[key] = EmaPlan(srcs, dsts)
+    plan.run(m)
+
+
+# ------------------------------------------------------------------------ Normalize
+class _L2Norm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, eps):
+        xc = _f32c(x)
+        y = torch.empty_like(xc)
+        check(_lib.load().moma_l2norm_fwd(_p(xc), _p(y), xc.shape[0], xc.shape[1], eps, _stream()))
+        ctx.save_for_backward(xc)
+        ctx.eps = eps
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (xc,) = ctx.saved_tensors
+        g = _f32c(g)
+        dx = torch.empty_like(xc)
+        check(_lib.load().moma_l2norm_bwd(_p(xc), _p(g), _p(dx), xc.shape[0], xc.shape[1], ctx.eps, _stream()))
+        return dx, None
+
+
+def l2_normalize(x: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
+    """F.normalize(x, p=2, dim=1) for a 2-D CUDA tensor."""
+    _need_cuda(x)
+    if x.dim() != 2 or x.shape[1] % 4 != 0:
+        raise RuntimeError("moma_b200.l2_normalize: expects [rows, D] with D % 4 == 0")
+    return _L2Norm.apply(x, eps)
+
+
+# -------------------------------------------------------------------------- enqueue
+def cast_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
+    check(_lib.load().moma_cast_bf16(_p(src), _p(dst), src.numel(), _stream()))
+
+
+def enqueue(keys: torch.Tensor, queue: torch.Tensor, shadow: Optional[torch.Tensor], K: int, index: int,
+            rank: int = 0, world: int = 1, normalize: bool = False, eps: float = 1e-12,
+            index_dev: Optional[torch.Tensor] = None) -> None:
+    """queue[(index + j) % K] = keys[j]  (mem_moco.py:17-27), cyclically sharded when world > 1."""
+    _need_cuda(keys, queue, shadow)
+    keys = _f32c(keys.detach())
+    check(_lib.load().moma_enqueue(_p(keys), keys.shape[0], keys.shape[1], _p(queue), _p(shadow), K, int(index),
+                                   _p(index_dev), rank, world, int(normalize), eps, _stream()))
+
+
+def enqueue_ids(n: int, index: int, K: int, device) -> torch.Tensor:
+    out = torch.empty(n, dtype=torch.int64, device=device)
+    check(_lib.load().moma_enqueue_ids(n, int(index), None, K, _p(out), _stream()))
+    return out
+
+
+# ---------------------------------------------------------------------------- InfoNCE
+def nce_num_splits(B: int, D: int, K_local: int, dtype: int) -> int:
+    return int(_lib.load().moma_nce_num_splits(B, D, K_local, dtype))
+
+
+def nce_partial(q: torch.Tensor, queue: torch.Tensor, inv_T: float, dtype: int, n_splits: Optional[int] = None):
+    """Per-split partials (m, l, mmax, O) of q against the local queue rows."""
+    B, D = q.shape
+    K_local = queue.shape[0]
+    if n_splits is None:
+        n_splits = nce_num_splits(B, D, K_local, dtype)
+    dev = q.device
+    stats = torch.empty((3, n_splits, B), dtype=torch.float32, device=dev)
+    O = torch.empty((n_splits, B, D), dtype=torch.float32, device=dev)
+    check(_lib.load().moma_nce_partial(_p(q), _p(queue), B, D, K_local, inv_T, dtype, n_splits,
+                                       _p(stats[0]), _p(stats[1]), _p(stats[2]), _p(O), _stream()))
+    return stats, O
+
+
+def nce_combine(stats: torch.Tensor, O: torch.Tensor, q_f32: torch.Tensor, k_f32: torch.Tensor, inv_T: float):
+    """Merge partials (+ positive column) ->
+    (loss_rows [B], dq_unit [B, D], pos_is_max [B] int32, max_logit [B])."""
+    n_parts, B = stats.shape[1], stats.shape[2]
+    D = O.shape[2]
+    dev = q_f32.device
+    rows = torch.empty(B, dtype=torch.float32, device=dev)
+    dq = torch.empty((B, D), dtype=torch.float32, device=dev)
+    pim = torch.empty(B, dtype=torch.int32, device=dev)
+    mx = torch.empty(B, dtype=torch.float32, device=dev)
+    check(_lib.load().moma_nce_combine(_p(stats[0]), _p(stats[1]), _p(stats[2]), _p(O), n_parts, _p(q_f32),
+                                       _p(k_f32), B, D, inv_T, _p(rows), _p(dq), _p(pim), _p(mx), _stream()))
+    return rows, dq, pim, mx
+
+
+def nce_operands(q: torch.Tensor, k: torch.Tensor, precision: str):
+    """Operands in the arithmetic type of the chosen mode: (q_op, dtype, q_f32, k_f32).
+    In bf16 mode q/k are rounded to bf16 (the fp32 copies hold the rounded values)."""
+    q32, k32 = _f32c(q.detach()), _f32c(k.detach())
+    if precision == "bf16":
+        qb = q32.to(torch.bfloat16)
+        return qb, BF16, qb.float(), k32.to(torch.bfloat16).float()
+    return q32, F32, q32, k32
+
+
+class _NceFused(torch.autograd.Function):
+    """rows[i] = LSE_i - l_i0 and, from the same pass over the queue, d rows[i] / d q_i."""
+
+    @staticmethod
+    def forward(ctx, q, k, queue_f32, queue_bf16, T, precision):
+        inv_T = 1.0 / T
+        q_op, dtype, q32, k32 = nce_operands(q, k, precision)
+        queue = queue_bf16 if dtype == BF16 else queue_f32
+        stats, O = nce_partial(q_op, queue, inv_T, dtype)
+        rows, dq_unit, pim, mx = nce_combine(stats, O, q32, k32, inv_T)
+        ctx.save_for_backward(dq_unit)
+        ctx.q_dtype = q.dtype
+        ctx.mark_non_differentiable(pim, mx)
+        return rows, pim, mx
+
+    @staticmethod
+    def backward(ctx, g, _gp, _gm):
+        (dq_unit,) = ctx.saved_tensors
+        return (g.unsqueeze(1) * dq_unit).to(ctx.q_dtype), None, None, None, None, None
+
+
+def nce_rows(q: torch.Tensor, k: torch.Tensor, queue_f32: torch.Tensor, queue_bf16: Optional[torch.Tensor],
+             T: float, precision: Optional[str] = None):
+    """Single-GPU fused InfoNCE: returns (rows [B] differentiable w.r.t. q, pos_is_max [B] int32,
+    max_logit [B])."""
+    _need_cuda(q, k, queue_f32)
+    precision = precision or _PRECISION
+    if precision == "bf16" and (queue_bf16 is None or not bf16_supported(q.shape[1])):
+        precision = "fp32"
+    return _NceFused.apply(q, k.detach(), queue_f32, queue_bf16, float(T), precision)
+
+
+def bf16_supported(D: int) -> bool:
+    """Shapes the tcgen05 kernel handles (see csrc/nce_tc.cu)."""
+    return bool(_lib.load().moma_has_tcgen05()) and D in (64, 128, 256)
+
+
+def fused_nce_supported(D: int) -> bool:
+    return D % 4 == 0 and D <= 512
+
+
+class _NceLogits(torch.autograd.Function):
+    """Dense logits [B, K+1] (mem_moco.py:29-49); backward = dense dlogits -> dq (k, queue detached)."""
+
+    @staticmethod
+    def forward(ctx, q, k, queue, T):
+        q32, k32 = _f32c(q), _f32c(k)
+        B, D = q32.shape
+        K = queue.shape[0]
+        out = torch.empty((B, K + 1), dtype=torch.float32, device=q.device)
+        dtype = BF16 if queue.dtype == torch.bfloat16 else F32
+        if dtype == BF16:
+            qo, ko = q32.to(torch.bfloat16), k32.to(torch.bfloat16)
+        else:
+            qo, ko = q32, k32
+        check(_lib.load().moma_nce_logits(_p(qo), _p(ko), _p(queue), B, D, K, T, dtype, _p(out), _stream()))
+        ctx.save_for_backward(k32, queue)
+        ctx.T = T
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        k32, queue = ctx.saved_tensors
+        g = g / ctx.T
+        dq = g[:, :1] * k32 + g[:, 1:] @ queue.float()      # escape hatch only: library GEMM
+        return dq, None, None, None
+
+
+def nce_logits(q, k, queue, T) -> torch.Tensor:
+    _need_cuda(q, k, queue)
+    return _NceLogits.apply(q, k.detach(), queue.detach(), float(T))
+
+
+def nce_logits_qk(q, k, T) -> torch.Tensor:
+    """mem_moco.py:51-66; tiny, differentiable through torch ops on the kernel's operands."""
+    _need_cuda(q, k)
+    q32, k32 = _f32c(q), _f32c(k.detach())
+    if q.requires_grad and torch.is_grad_enabled():
+        return (q32 * k32).sum(1) / T
+    out = torch.empty(q32.shape[0], dtype=torch.float32, device=q.device)
+    check(_lib.load().moma_nce_logits_qk(_p(q32), _p(k32), q32.shape[0], q32.shape[1], float(T), _p(out), _stream()))
+    return out
+
+
+# -------------------------------------------------------------------------- attention
+class _Attention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w_qkv, b_qkv, w_proj, b_proj, H, want_probs):
+        lib = _lib.load()
+        xc, wq, wp, bp = _f32c(x), _f32c(w_qkv), _f32c(w_proj), _f32c(b_proj)
+        bq = _f32c(b_qkv) if b_qkv is not None else None
+        N, C = xc.shape
+        dev = xc.device
+        y = torch.empty((N, C), dtype=torch.float32, device=dev)
+        qkv = torch.empty((N, 3 * C), dtype=torch.float32, device=dev)
+        o = torch.empty((N, C), dtype=torch.float32, device=dev)
+        lse = torch.empty((H, N), dtype=torch.float32, device=dev)
+        probs = torch.empty((1, H, N, N), dtype=torch.float32, device=dev) if want_probs else None
+        check(lib.moma_attn_fwd(_p(xc), _p(wq), _p(bq), _p(wp), _p(bp), N, C, H, _p(y), _p(qkv), _p(o), _p(lse),
+                                _p(probs), _stream()))
+        ctx.save_for_backward(xc, wq, wp, qkv, o, lse)
+        ctx.H = H
+        ctx.has_bq = b_qkv is not None
+        if want_probs:
+            ctx.mark_non_differentiable(probs)
+            return y, probs
+        return y
+
+    @staticmethod
+    def backward(ctx, gy, *unused):
+        lib = _lib.load()
+        xc, wq, wp, qkv, o, lse = ctx.saved_tensors
+        N, C = xc.shape
+        H = ctx.H
+        gy = _f32c(gy)
+        need = ctx.needs_input_grad
+        dev = xc.device
+        gx = torch.empty_like(xc) if need[0] else None
+        gwq = torch.empty_like(wq) if need[1] else None
+        gbq = torch.empty(3 * C, dtype=torch.float32, device=dev) if (need[2] and ctx.has_bq) else None
+        gwp = torch.empty_like(wp) if need[3] else None
+        gbp = torch.empty(C, dtype=torch.float32, device=dev) if need[4] else None
+        ws_bytes = int(lib.moma_attn_bwd_workspace_bytes(N, C, H))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(lib.moma_attn_bwd(_p(xc), _p(wq), _p(wp), _p(qkv), _p(o), _p(lse), _p(gy), N, C, H, _p(gx), _p(gwq),
+                                _p(gbq), _p(gwp), _p(gbp), _p(ws), ws_bytes, _stream()))
+        return gx, gwq, gbq, gwp, gbp, None, None
+
+
+def attention(x, w_qkv, b_qkv, w_proj, b_proj, num_heads: int, want_probs: bool = False):
+    """Attention.forward (criterion_moco_att.py:153-167) on x [N, C]."""
+    _need_cuda(x, w_qkv, w_proj)
+    if x.dim() != 2:
+        raise RuntimeError("moma_b200.attention: expects [N, C]")
+    return _Attention.apply(x, w_qkv, b_qkv, w_proj, b_proj, int(num_heads), bool(want_probs))
+
+
+def attention_supported(C: int, H: int) -> bool:
+    return C % H == 0 and (C // H) in (16, 32, 64, 128)
