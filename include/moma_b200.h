@@ -130,6 +130,11 @@ int moma_nce_combine(const float *part_m, const float *part_l, const float *part
                      int64_t B, int64_t D, float inv_T, float *loss_rows, float *dq_unit,
                      int32_t *pos_is_max, float *max_logit /* nullable: max_j l_ij */,
                      moma_stream_t stream);
+/* Fold `n_parts` partials into ONE partial per row (same (m, l, mmax, O) convention); used by
+ * the K-sharded queue before the cross-rank exchange. */
+int moma_nce_merge(const float *part_m, const float *part_l, const float *part_mmax,
+                   const float *part_O, int n_parts, int64_t B, int64_t D, float *out_m,
+                   float *out_l, float *out_mmax, float *out_O, moma_stream_t stream);
 /* Escape hatch / tests: materialise logits[B, K+1] = cat(q.k, q queue^T) / T
  * exactly as mem_moco.py:29-49 lays them out (row stride K+1). */
 int moma_nce_logits(const void *q, const void *kpos, const void *queue, int64_t B, int64_t D,
@@ -145,7 +150,7 @@ int moma_nce_logits_qk(const float *q, const float *kpos, int64_t B, int64_t D, 
  * x [N, C]; w_qkv [3C, C]; b_qkv [3C] or NULL; w_proj [C, C]; b_proj [C].
  * Saved for backward (caller-owned): qkv [N, 3C], o [N, C] (merged heads),
  * lse [H, N].  attn_probs (nullable, [H, N, N]) is only for Attention_viz.
- * head_dim = C / H must be one of 16, 32, 64, 128.
+ * head_dim = C / H must be one of 8, 16, 32, 64, 128.
  * ------------------------------------------------------------------------- */
 int moma_attn_fwd(const float *x, const float *w_qkv, const float *b_qkv, const float *w_proj,
                   const float *b_proj, int64_t N, int64_t C, int H, float *y, float *qkv,

@@ -105,7 +105,9 @@ constexpr int kLdP = kAC + 4;
 template <int HD> struct AttnCfg {
     static constexpr int LD = HD + 4;                       // padded smem row (floats)
     static constexpr int CPL = HD >= 32 ? HD / 32 : 1;      // output columns per lane
-    static constexpr int RPL = HD >= 32 ? 8 : 4;            // output rows per lane
+    static constexpr int RPL = HD >= 32 ? 8 : HD / 4;       // output rows per lane (32/HD row groups)
+    __device__ static int roff(int lane) { return HD >= 32 ? 0 : (lane / HD) * RPL; }
+    __device__ static int cbase(int lane) { return HD >= 32 ? lane : (lane % HD); }
 };
 
 // load `rows` token rows x HD columns (global row stride ldg) into smem [rows][HD+4]
@@ -147,8 +149,8 @@ __device__ __forceinline__ void acc_tile(const float* p_s, const float* v_s, int
                                          float (&acc)[AttnCfg<HD>::RPL][AttnCfg<HD>::CPL]) {
     using Cfg = AttnCfg<HD>;
     constexpr int LD = Cfg::LD;
-    const int rbase = warp * 8 + (HD >= 32 ? 0 : (lane >> 4) * 4);
-    const int cbase = HD >= 32 ? lane : (lane & 15);
+    const int rbase = warp * 8 + Cfg::roff(lane);
+    const int cbase = Cfg::cbase(lane);
 #pragma unroll 2
     for (int j = 0; j < kAC; j += 4) {
         float vv[4][Cfg::CPL];
@@ -212,7 +214,7 @@ attn_fwd_kernel(const float* __restrict__ qkv, int N, int C, float scale, float*
             l_run[r] = l_run[r] * corr[r] + warp_sum(p0 + p1);
             m_run[r] = m_new;
         }
-        const int roff = HD >= 32 ? 0 : (lane >> 4) * 4;
+        const int roff = Cfg::roff(lane);
 #pragma unroll
         for (int r = 0; r < Cfg::RPL; ++r) {
             // corr is warp-uniform per row; pick this lane's rows
@@ -225,8 +227,8 @@ attn_fwd_kernel(const float* __restrict__ qkv, int N, int C, float scale, float*
         __syncwarp();
         acc_tile<HD>(p_s, v_s, warp, lane, acc);
     }
-    const int roff = HD >= 32 ? 0 : (lane >> 4) * 4;
-    const int cbase = HD >= 32 ? lane : (lane & 15);
+    const int roff = Cfg::roff(lane);
+    const int cbase = Cfg::cbase(lane);
 #pragma unroll
     for (int r = 0; r < Cfg::RPL; ++r) {
         float lr = l_run[0];
@@ -326,8 +328,8 @@ attn_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
         __syncwarp();
         acc_tile<HD>(p_s, k_s, warp, lane, acc);
     }
-    const int roff = HD >= 32 ? 0 : (lane >> 4) * 4;
-    const int cbase = HD >= 32 ? lane : (lane & 15);
+    const int roff = Cfg::roff(lane);
+    const int cbase = Cfg::cbase(lane);
 #pragma unroll
     for (int r = 0; r < Cfg::RPL; ++r) {
         const int row = i0 + warp * 8 + roff + r;
@@ -389,8 +391,8 @@ attn_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
         acc_tile<HD>(p_s, do_s, warp, lane, acc_v);
         acc_tile<HD>(ds_s, q_s, warp, lane, acc_k);
     }
-    const int roff = HD >= 32 ? 0 : (lane >> 4) * 4;
-    const int cbase = HD >= 32 ? lane : (lane & 15);
+    const int roff = Cfg::roff(lane);
+    const int cbase = Cfg::cbase(lane);
 #pragma unroll
     for (int r = 0; r < Cfg::RPL; ++r) {
         const int row = j0 + warp * 8 + roff + r;
@@ -431,8 +433,8 @@ static int check_attn(const char* who, int64_t N, int64_t C, int H) {
     MOMA_REQUIRE(N > 0 && C > 0 && H > 0, MOMA_ERR_INVALID, "%s: bad shape N=%lld C=%lld H=%d", who, (long long)N, (long long)C, H);
     MOMA_REQUIRE(C % H == 0, MOMA_ERR_INVALID, "%s: C=%lld not divisible by H=%d", who, (long long)C, H);
     const int64_t hd = C / H;
-    MOMA_REQUIRE(hd == 16 || hd == 32 || hd == 64 || hd == 128, MOMA_ERR_UNSUPPORTED,
-                 "%s: head_dim=%lld unsupported (16, 32, 64, 128)", who, (long long)hd);
+    MOMA_REQUIRE(hd == 8 || hd == 16 || hd == 32 || hd == 64 || hd == 128, MOMA_ERR_UNSUPPORTED,
+                 "%s: head_dim=%lld unsupported (8, 16, 32, 64, 128)", who, (long long)hd);
     MOMA_REQUIRE(N < (1 << 24) && C <= 8192, MOMA_ERR_UNSUPPORTED, "%s: shape too large", who);
     return MOMA_OK;
 }
@@ -454,6 +456,7 @@ extern "C" __attribute__((visibility("default"))) int moma_attn_fwd(const float*
     const float scale = 1.0f / sqrtf((float)hd);
     sgemm(x, C, 1, w_qkv, C, 1, b_qkv, qkv, 3 * C, n, 3 * c, c, st);
     switch (hd) {
+        case 8: launch_fwd<8>(qkv, n, c, H, scale, o, lse, st); break;
         case 16: launch_fwd<16>(qkv, n, c, H, scale, o, lse, st); break;
         case 32: launch_fwd<32>(qkv, n, c, H, scale, o, lse, st); break;
         case 64: launch_fwd<64>(qkv, n, c, H, scale, o, lse, st); break;
@@ -498,6 +501,7 @@ extern "C" __attribute__((visibility("default"))) int moma_attn_bwd(const float*
     sgemm(grad_y, C, 1, w_proj, 1, C, nullptr, dO, C, n, c, c, st);
     attn_delta_kernel<<<(n * H + 3) / 4, 128, 0, st>>>(dO, o, n, c, H, delta);
     switch (hd) {
+        case 8: launch_bwd<8>(qkv, dO, lse, delta, n, c, H, scale, dqkv, st); break;
         case 16: launch_bwd<16>(qkv, dO, lse, delta, n, c, H, scale, dqkv, st); break;
         case 32: launch_bwd<32>(qkv, dO, lse, delta, n, c, H, scale, dqkv, st); break;
         case 64: launch_bwd<64>(qkv, dO, lse, delta, n, c, H, scale, dqkv, st); break;

@@ -244,6 +244,36 @@ nce_combine_kernel(const float* __restrict__ part_m, const float* __restrict__ p
     }
 }
 
+// ------------------------------------------------------------------ merge (splits -> 1 partial)
+// Used by the K-sharded queue: each rank folds its local splits into one partial per query row
+// before the cross-rank exchange, so (D + 3) floats per row travel instead of n_splits times that.
+__global__ void __launch_bounds__(128)
+nce_merge_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l,
+                 const float* __restrict__ part_mmax, const float* __restrict__ part_O, int n_parts,
+                 int B, int D, float* __restrict__ out_m, float* __restrict__ out_l,
+                 float* __restrict__ out_mmax, float* __restrict__ out_O) {
+    const int row = blockIdx.x, tid = threadIdx.x;
+    float mref = -CUDART_INF_F, mtrue = -CUDART_INF_F;
+    for (int s = 0; s < n_parts; ++s) {
+        mref = fmaxf(mref, part_m[(int64_t)s * B + row]);
+        mtrue = fmaxf(mtrue, part_mmax[(int64_t)s * B + row]);
+    }
+    float l = 0.f;
+    for (int d0 = 0; d0 < D; d0 += 128) {
+        const int d = d0 + tid;
+        float o = 0.f;
+        for (int s = 0; s < n_parts; ++s) {
+            const int64_t base = (int64_t)s * B + row;
+            const float ms = part_m[base];
+            const float w = (ms == -CUDART_INF_F) ? 0.f : expf(ms - mref);
+            if (d0 == 0 && tid == 0) l += w * part_l[base];
+            if (d < D) o += w * part_O[base * D + d];
+        }
+        if (d < D) out_O[(int64_t)row * D + d] = o;
+    }
+    if (tid == 0) { out_m[row] = mref; out_l[row] = l; out_mmax[row] = mtrue; }
+}
+
 // ------------------------------------------------------------------ materialise
 template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
@@ -381,6 +411,18 @@ extern "C" __attribute__((visibility("default"))) int moma_nce_combine(const flo
         part_m, part_l, part_mmax, part_O, n_parts, q_f32, kpos_f32, (int)B, (int)D, inv_T,
         loss_rows, dq_unit, pos_is_max, max_logit);
     MOMA_CUDA_LAUNCH_CHECK("nce_combine");
+    return MOMA_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int moma_nce_merge(
+    const float* part_m, const float* part_l, const float* part_mmax, const float* part_O, int n_parts,
+    int64_t B, int64_t D, float* out_m, float* out_l, float* out_mmax, float* out_O, moma_stream_t stream) {
+    MOMA_REQUIRE(B > 0 && D > 0 && n_parts > 0, MOMA_ERR_INVALID, "nce_merge: bad shape");
+    MOMA_REQUIRE(part_m && part_l && part_mmax && part_O && out_m && out_l && out_mmax && out_O,
+                 MOMA_ERR_INVALID, "nce_merge: null pointer");
+    nce_merge_kernel<<<(unsigned)B, 128, 0, as_stream(stream)>>>(part_m, part_l, part_mmax, part_O, n_parts,
+                                                                (int)B, (int)D, out_m, out_l, out_mmax, out_O);
+    MOMA_CUDA_LAUNCH_CHECK("nce_merge");
     return MOMA_OK;
 }
 

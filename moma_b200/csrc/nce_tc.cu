@@ -171,6 +171,9 @@ struct __align__(8) Bars {
     uint64_t s_full[2];
     uint64_t p_full[2];
     uint64_t pv_done[2];
+    uint64_t o_final;      // committed once after the last PV: the epilogue must not reuse the
+                           // per-tile pv_done phases (with NQ == 1 a warp can be two phases ahead
+                           // of it, and a parity wait would alias)
     uint32_t tmem_base;
     uint32_t pad;
 };
@@ -232,6 +235,7 @@ nce_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     auto b_s_full = [&](int b) { return smem_u32(&bars->s_full[b]); };
     auto b_p_full = [&](int b) { return smem_u32(&bars->p_full[b]); };
     auto b_pv_done = [&](int g) { return smem_u32(&bars->pv_done[g]); };
+    const uint32_t b_o_final = smem_u32(&bars->o_final);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_q);
@@ -239,6 +243,7 @@ nce_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         mbar_init(b_q_full, 1);
         for (int s = 0; s < kStages; ++s) { mbar_init(b_kv_full(s), 1); mbar_init(b_kv_empty(s), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(b_s_full(b), 1); mbar_init(b_p_full(b), 128); mbar_init(b_pv_done(b), 1); }
+        mbar_init(b_o_final, 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(smem_u32(&bars->tmem_base), kTmemCols);
@@ -339,6 +344,7 @@ nce_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                     }
                 }
             }
+            umma_commit(b_o_final);
         }
       }
     } else if ((warp - 4) / 4 < nq_active) {
@@ -384,7 +390,16 @@ nce_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
             m_true = fmaxf(m_true, mx);
             const bool need = mx > m_ref + kLazyTau;                 // always true on the first tile
+#ifdef MOMA_TC_ALWAYS_RESCALE
+            if (i > 0) {
+#else
             if (i > 0 && __any_sync(0xffffffffu, need)) {
+#endif
+                if (dbg_S != nullptr && row < B) {
+                    float* info = dbg_S + ((long long)B + row) * BN;
+                    info[0] += 1.f; info[1] += need ? 1.f : 0.f; info[3] = (float)i;
+                    info[2] = need ? ex2(m_ref - mx) : 1.0f;
+                }
                 // rare: the running max grew by > 2^8 -> rescale O and l to the new reference
                 mbar_wait(b_pv_done(g), (i - 1) & 1, 202);
                 tc_fence_after();
@@ -426,7 +441,7 @@ nce_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         }
 
         // epilogue: O (TMEM) -> part_O, stats
-        mbar_wait(b_pv_done(g), (nt - 1) & 1, 203);
+        mbar_wait(b_o_final, 0, 203);
         tc_fence_after();
         const long long orow = (long long)split * B + row;
 #pragma unroll 1

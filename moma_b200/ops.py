@@ -193,6 +193,19 @@ def nce_combine(stats: torch.Tensor, O: torch.Tensor, q_f32: torch.Tensor, k_f32
     return rows, dq, pim, mx
 
 
+def nce_merge(stats: torch.Tensor, O: torch.Tensor):
+    """Fold the split partials [3, S, B] / [S, B, D] into one partial per row: ([3, 1, B], [1, B, D])."""
+    n_parts, B = stats.shape[1], stats.shape[2]
+    D = O.shape[2]
+    if n_parts == 1:
+        return stats, O
+    out_s = torch.empty((3, 1, B), dtype=torch.float32, device=O.device)
+    out_O = torch.empty((1, B, D), dtype=torch.float32, device=O.device)
+    check(_lib.load().moma_nce_merge(_p(stats[0]), _p(stats[1]), _p(stats[2]), _p(O), n_parts, B, D,
+                                     _p(out_s[0]), _p(out_s[1]), _p(out_s[2]), _p(out_O), _stream()))
+    return out_s, out_O
+
+
 def nce_operands(q: torch.Tensor, k: torch.Tensor, precision: str):
     """Operands in the arithmetic type of the chosen mode: (q_op, dtype, q_f32, k_f32).
     In bf16 mode q/k are rounded to bf16 (the fp32 copies hold the rounded values)."""
@@ -341,4 +354,4 @@ def attention(x, w_qkv, b_qkv, w_proj, b_proj, num_heads: int, want_probs: bool 
 
 
 def attention_supported(C: int, H: int) -> bool:
-    return C % H == 0 and (C // H) in (16, 32, 64, 128)
+    return C % H == 0 and (C // H) in (8, 16, 32, 64, 128)

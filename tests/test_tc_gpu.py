@@ -47,12 +47,15 @@ def run_tc(lib, q, queue, T, n_splits=None, want_dbg=False):
     BN = 64 if D == 256 else 128
     stats = torch.full((3, n_splits, B), float("nan"), device="cuda")
     Op = torch.full((n_splits, B, D), float("nan"), device="cuda")
-    dbg = torch.full((B, BN), float("nan"), device="cuda") if want_dbg else None
+    dbg = torch.zeros((2 * B, BN), device="cuda") if want_dbg else None
     check(lib.moma_debug_nce_tc(qb.data_ptr(), kb.data_ptr(), B, D, K, 1.0 / T, n_splits, stats[0].data_ptr(),
                                 stats[1].data_ptr(), stats[2].data_ptr(), Op.data_ptr(),
                                 None if dbg is None else dbg.data_ptr(), torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     assert lib.moma_debug_tc_error() == 0
+    if dbg is not None:
+        run_tc.info = dbg[B:].clone()
+        dbg = dbg[:B]
     return stats, Op, dbg, qb, kb
 
 
