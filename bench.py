@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- MoMA criterion step throughput (samples/s) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2|C3|C5]
+
+A "step" is one pass of the hot path over one synthetic batch (level L1):
+backbone EMA (student -> momentum twin) + projection heads + 3x attention + fused InfoNCE
+logits/CE forward AND backward (to d loss / d feat_s and the criterion parameters) + key
+all-gather (N > 1) + ring enqueue.  Backbones are outside the path: inputs are their features.
+
+Default workload = BASELINE.json configs[1] (C2): ResNet-50 teacher -> ResNet-18 student,
+batch 256 per GPU, D = 128, K = 16384, bf16 InfoNCE operands.  With N > 1 the per-GPU batch is
+fixed (weak scaling) and the queue is sharded by K across ranks.
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput; `e2e` goes through the
+public module API with HOST (pinned) inputs and a host read of the loss inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CONFIGS = {
+    # name: per-GPU batch, s_dim, t_dim, D, K, heads, description
+    "C1": dict(B=32, s_dim=512, t_dim=2048, D=128, K=4096, H=4,
+               desc="C1 R18<-R50 B32 D128 K4096 (the reference's CPU-runnable case)"),
+    "C2": dict(B=256, s_dim=512, t_dim=2048, D=128, K=16384, H=4,
+               desc="C2 MoMA criterion step, ResNet-50 teacher -> ResNet-18 student, B256/GPU D128 K16384 bf16"),
+    "C3": dict(B=512, s_dim=512, t_dim=2048, D=128, K=65536, H=8,
+               desc="C3 large memory bank K65536, 8 heads, B512/GPU D128"),
+    "C5": dict(B=1024, s_dim=384, t_dim=768, D=256, K=131072, H=4,
+               desc="C5 ViT-S<-ViT-B features, B1024/GPU D256 K131072"),
+}
+T_NCE, ALPHA, SEED = 0.15, 0.999, 12345
+
+
+def resnet18_param_shapes(num_classes=4):
+    """Parameter shapes of the reference ResNet-18 (models/resnet_imagenet.py; 62 tensors,
+    11,178,564 elements) in parameters() order -- the EMA pair is (student, same-architecture
+    momentum twin) because the reference's momentum_update raises on heterogeneous pairs."""
+    shapes = [(64, 3, 7, 7), (64,), (64,)]
+    cin = 64
+    for cout, stride in ((64, 1), (128, 2), (256, 2), (512, 2)):
+        for blk in range(2):
+            shapes += [(cout, cin if blk == 0 else cout, 3, 3), (cout,), (cout,), (cout, cout, 3, 3), (cout,), (cout,)]
+            if blk == 0 and (stride != 1 or cin != cout):
+                shapes += [(cout, cin, 1, 1), (cout,), (cout,)]
+        cin = cout
+    shapes += [(num_classes, 512), (num_classes,)]
+    return shapes
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.stop_flag, self.max_mhz = [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksEventReasonHwPowerBrakeSlowdown: "hw_power_brake"} if hasattr(
+            nv, "nvmlClocksEventReasonHwSlowdown") else {}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------- our arm
+class CriterionStep:
+    """The criterion step through the public (reference-shaped) module API of moma_b200."""
+
+    def __init__(self, cfg, rank, world, device):
+        from argparse import Namespace
+
+        import moma_b200
+        from moma_b200 import CMO, ContrastTrainer, build_mem
+        self.cfg, self.rank, self.world, self.dev = cfg, rank, world, device
+        moma_b200.set_precision("bf16")
+        torch.manual_seed(SEED)                       # same seed on every rank -> identical init (reference :241-246)
+        opt = Namespace(head="mlp", s_dim=cfg["s_dim"], t_dim=cfg["t_dim"], feat_dim=cfg["D"], attn="self", mem="MoCo",
+                        nce_k=cfg["K"], nce_t=T_NCE, alpha=ALPHA, num_heads=cfg["H"], shard_queue=world > 1)
+        self.opt = opt
+        self.contrast = build_mem(opt).to(device)
+        self.crit = CMO(opt).to(device)
+        self.trainer = ContrastTrainer
+        shapes = resnet18_param_shapes()
+        self.student = torch.nn.ParameterList([torch.nn.Parameter(torch.randn(*s)) for s in shapes]).to(device)
+        self.teacher = torch.nn.ParameterList([torch.nn.Parameter(torch.randn(*s)) for s in shapes]).to(device)
+        self.ema_elems = sum(p.numel() for p in self.student)
+        self.ce = torch.nn.CrossEntropyLoss()
+        self.head_ema = cfg["s_dim"] == cfg["t_dim"]
+        self.params = [p for n, p in self.crit.named_parameters() if not n.startswith("embed_t")]
+        torch.manual_seed(SEED + 1 + rank)            # data differs per rank
+        B = cfg["B"]
+        self.feat_s = torch.randn(B, cfg["s_dim"], device=device, requires_grad=True)
+        self.feat_t = torch.randn(B, cfg["t_dim"], device=device)
+        self.host_s = torch.randn(B, cfg["s_dim"]).pin_memory()
+        self.host_t = torch.randn(B, cfg["t_dim"]).pin_memory()
+        self.h2d_bytes = (self.host_s.numel() + self.host_t.numel()) * 4
+        self.loss = None
+
+    def step(self, feat_s=None, feat_t=None):
+        """helper/loops_moma.py:308-335 + :360 (backward) on features."""
+        crit, opt = self.crit, self.opt
+        feat_s = self.feat_s if feat_s is None else feat_s
+        feat_t = self.feat_t if feat_t is None else feat_t
+        self.trainer.momentum_update(self.student, self.teacher, opt.alpha)
+        if self.head_ema:
+            self.trainer.momentum_update(crit.embed_s, crit.embed_t, opt.alpha)
+        with torch.no_grad():
+            k = crit.embed_t(feat_t)
+        all_k = self.trainer._global_gather(k) if self.world > 1 else k
+        f_s = crit.embed_s(feat_s)
+        f_s = crit.atts_q(f_s)
+        k = crit.atts_k(k)
+        all_k = crit.atts_queue(all_k)
+        output = self.contrast(q=f_s, k=k, all_k=all_k)
+        losses, accs = self.trainer._compute_loss_accuracy(output[:-1], output[-1], self.ce)
+        for p in self.params:
+            p.grad = None
+        feat_s.grad = None
+        losses[0].backward()
+        self.loss = losses[0]
+        return losses[0]
+
+    def step_e2e(self):
+        fs = self.host_s.to(self.dev, non_blocking=True).requires_grad_()
+        ft = self.host_t.to(self.dev, non_blocking=True)
+        return float(self.step(fs, ft).item())          # D2H read of the loss inside the timed region
+
+
+def run_ours(args, cfg, rank, world, local_rank):
+    import torch.distributed as dist
+
+    import moma_b200
+    from moma_b200 import _lib, ops
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    lib = _lib.load()
+    cs = CriterionStep(cfg, rank, world, device)
+    B, D, K = cfg["B"], cfg["D"], cfg["K"]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """Per-step CUDA-event timing on the launching stream (L2 flushed before each step), summed."""
+        evs = []
+        barrier()
+        for _ in range(steps):
+            if flush is not None:
+                flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        if world > 1:
+            t = torch.tensor([ms], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # warm-up (also builds the EMA plan, TMA descriptors, bf16 shadow, cuBLAS handles)
+    for _ in range(max(args.warmup, 3)):
+        cs.step()
+    torch.cuda.synchronize()
+
+    # ---- per-kernel events for the roofline (nce partial / ema), collected during the timed steps
+    prof = {"nce": [], "ema": []}
+    orig_partial, orig_ema_run = ops.nce_partial, ops.EmaPlan.run
+
+    def partial_hook(*a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); out = orig_partial(*a, **k); e1.record()
+        prof["nce"].append((e0, e1))
+        return out
+
+    def ema_hook(self, m):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); orig_ema_run(self, m); e1.record()
+        if self.elements > 1_000_000:
+            prof["ema"].append((e0, e1))
+
+    ops.nce_partial, ops.EmaPlan.run = partial_hook, ema_hook
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    lib.moma_debug_launch_count(1)
+    total_ms = timed(cs.step, args.steps)
+    launches = int(lib.moma_debug_launch_count(1))
+    sampler.stop_flag = True
+    sampler.join(timeout=1)
+    nce_us = 1e3 * sum(a.elapsed_time(b) for a, b in prof["nce"]) / max(len(prof["nce"]), 1)
+    ema_us = 1e3 * sum(a.elapsed_time(b) for a, b in prof["ema"]) / max(len(prof["ema"]), 1)
+    ops.nce_partial, ops.EmaPlan.run = orig_partial, orig_ema_run
+
+    # ---- end to end: host inputs, H2D + D2H inside the timed region
+    for _ in range(3):
+        cs.step_e2e()
+    e2e_ms = timed(cs.step_e2e, args.steps)
+
+    ms_per_step = total_ms / args.steps
+    value = B * world / (ms_per_step * 1e-3)
+    e2e_value = B * world / (e2e_ms / args.steps * 1e-3)
+
+    # ---- rooflines (algorithmic work per launch)
+    n_q = B * world                                   # queries scored per rank (all-gathered)
+    k_local = K // world
+    nce_flop = 4.0 * n_q * k_local * D                # S = Q.Queue^T and P.Queue, 2 FLOP/MAC each
+    ema_bytes = 12.0 * cs.ema_elems                   # read ema, read src, write ema (fp32)
+    tf_peak = peaks.get("bf16_tflops_sustained", 1421.9)
+    bw_peak = peaks.get("hbm_gbs", 6452.2)
+    roof_nce = {"kernel": "nce_tc_kernel (tcgen05 InfoNCE logits+CE fwd/bwd)", "bound": "tensor",
+                "achieved": nce_flop / (nce_us * 1e-6) / 1e12 if nce_us else None, "peak": tf_peak, "unit": "TFLOP/s",
+                "frac": (nce_flop / (nce_us * 1e-6) / 1e12 / tf_peak) if nce_us else None, "traffic": None,
+                "us_per_launch": nce_us, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback"}
+    roof_ema = {"kernel": "ema_multi_kernel (momentum update)", "bound": "hbm",
+                "achieved": ema_bytes / (ema_us * 1e-6) / 1e9 if ema_us else None, "peak": bw_peak, "unit": "GB/s",
+                "frac": (ema_bytes / (ema_us * 1e-6) / 1e9 / bw_peak) if ema_us else None, "traffic": None,
+                "us_per_launch": ema_us, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback"}
+    dominant = roof_ema if ema_us >= nce_us else roof_nce
+    other = roof_nce if dominant is roof_ema else roof_ema
+
+    out = {
+        "metric": "MoMA criterion samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": cfg["desc"], "global_batch": B * world, "feat_dim": D, "queue_K": K,
+                   "s_dim": cfg["s_dim"], "t_dim": cfg["t_dim"], "heads": cfg["H"], "nce_t": T_NCE, "alpha": ALPHA,
+                   "head": "mlp", "attn": "self", "ema_pair": "ResNet-18 student -> ResNet-18 momentum twin (11.18M)",
+                   "queue": "replicated" if world == 1 else f"sharded by K over {world} ranks (cyclic)",
+                   "l2": "no flush" if args.no_flush else "L2 flushed (256 MiB write) before every step; per-step CUDA events summed",
+                   "timed_region": "EMA + heads + 3x attention + fused InfoNCE/CE fwd+bwd + enqueue (criterion step, L1)"},
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": cs.h2d_bytes, "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches,
+        "gpu_launches_per_step": launches / args.steps,
+        "roofline": dominant, "roofline_other": other,
+        "clocks": sampler.summary(),
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(cfg, budget_s=args.cpu_seconds)
+    return out
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_baseline(cfg, budget_s=12.0):
+    """The reference's CPU path (oracle/torch_port.py, the pinned port of the reference op sequence)
+    on the host cores: bounded sample of the same workload."""
+    from oracle.torch_port import PortCriterionStep
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    port = PortCriterionStep(cfg["s_dim"], cfg["t_dim"], cfg["D"], cfg["K"], T_NCE, ALPHA, cfg["H"],
+                             resnet18_param_shapes(), seed=SEED)
+    B = cfg["B"]
+    torch.manual_seed(SEED + 1)
+    fs = torch.randn(B, cfg["s_dim"], requires_grad=True)
+    ft = torch.randn(B, cfg["t_dim"])
+    for _ in range(2):
+        port.step(fs, ft)
+    times = []
+    t_end = time.perf_counter() + budget_s
+    while len(times) < 5 or (time.perf_counter() < t_end and len(times) < 400):
+        t0 = time.perf_counter()
+        port.step(fs, ft)
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    return {"value": B / med, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{len(times)} full criterion steps of the same workload (median {med*1e3:.2f} ms/step), fp32, "
+                      f"torch {torch.__version__} CPU kernels", "ms_per_step": med * 1e3}
+
+
+def run_reference(args, cfg, rank, world):
+    if rank != 0:
+        return None
+    steps = max(args.steps, 1)
+    from oracle.torch_port import PortCriterionStep
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    port = PortCriterionStep(cfg["s_dim"], cfg["t_dim"], cfg["D"], cfg["K"], T_NCE, ALPHA, cfg["H"],
+                             resnet18_param_shapes(), seed=SEED)
+    B = cfg["B"]
+    torch.manual_seed(SEED + 1)
+    fs = torch.randn(B, cfg["s_dim"], requires_grad=True)
+    ft = torch.randn(B, cfg["t_dim"])
+    steps = min(steps, 200)
+    for _ in range(min(max(args.warmup, 1), 5)):
+        port.step(fs, ft)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        port.step(fs, ft)
+    dt = time.perf_counter() - t0
+    value = B * steps / dt
+    return {
+        "impl": "reference", "metric": "MoMA criterion samples/sec", "value": value, "unit": "samples/s",
+        "n_gpus": world, "steps": steps, "warmup": min(max(args.warmup, 1), 5), "ms_per_step": dt / steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["desc"], "global_batch": B, "feat_dim": cfg["D"], "queue_K": cfg["K"],
+                   "note": "reference CPU path (pinned torch port of the reference op sequence), one replica on rank 0"},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{steps} full criterion steps, fp32, all host threads"},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
+    ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+
+    if args.impl == "reference":
+        out = run_reference(args, cfg, rank, world)
+        if out is not None:
+            print(json.dumps(out), flush=True)
+        return
+
+    import torch.distributed as dist
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    out = run_ours(args, cfg, rank, world, local_rank)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -176,6 +176,8 @@ int moma_debug_nce_tc(const void *q, const void *queue, int64_t B, int64_t D, in
                       float inv_T, int n_splits, float *part_m, float *part_l, float *part_mmax,
                       float *part_O, float *dbg_S, moma_stream_t stream);
 int moma_debug_tc_error(void);
+/* number of kernels this library has launched in this process (optionally reset to 0) */
+long long moma_debug_launch_count(int reset);
 
 #ifdef __cplusplus
 }

@@ -2,7 +2,11 @@
 #include <stdarg.h>
 #include "common.cuh"
 
+#include <atomic>
 namespace moma {
+
+static std::atomic<long long> g_launches{0};
+void note_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 static thread_local char g_err[512] = "";
 
@@ -27,6 +31,9 @@ int sm_count() {
 
 }  // namespace moma
 
+extern "C" __attribute__((visibility("default"))) long long moma_debug_launch_count(int reset) {
+    return reset ? moma::g_launches.exchange(0) : moma::g_launches.load();
+}
 extern "C" __attribute__((visibility("default"))) int moma_abi_version(void) { return MOMA_ABI_VERSION; }
 extern "C" __attribute__((visibility("default"))) const char* moma_last_error(void) { return moma::g_err; }
 

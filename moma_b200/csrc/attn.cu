@@ -468,6 +468,7 @@ extern "C" __attribute__((visibility("default"))) int moma_attn_fwd(const float*
     }
     sgemm(o, C, 1, w_proj, C, 1, b_proj, y, C, n, c, c, st);
     MOMA_CUDA_LAUNCH_CHECK("attn_fwd");
+    note_launches(attn_probs ? 4 : 3);
     return MOMA_OK;
 }
 
@@ -512,5 +513,7 @@ extern "C" __attribute__((visibility("default"))) int moma_attn_bwd(const float*
     if (grad_b_qkv) colsum_kernel<<<(3 * c + 31) / 32, 256, 0, st>>>(dqkv, n, 3 * c, grad_b_qkv);
     if (grad_x) sgemm(dqkv, 3 * C, 1, w_qkv, 1, C, nullptr, grad_x, C, n, c, 3 * c, st);
     MOMA_CUDA_LAUNCH_CHECK("attn_bwd");
+    note_launches(4 + (grad_w_proj != nullptr) + (grad_b_proj != nullptr) + (grad_w_qkv != nullptr) +
+                  (grad_b_qkv != nullptr) + (grad_x != nullptr));
     return MOMA_OK;
 }

@@ -29,7 +29,8 @@ int fail(int code, const char* fmt, ...);
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline cudaStream_t as_stream(moma_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
-int sm_count();   // cached multiprocessor count of the current device (148 on B200)
+int sm_count();
+void note_launches(int n);   // launch counter behind moma_debug_launch_count()   // cached multiprocessor count of the current device (148 on B200)
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

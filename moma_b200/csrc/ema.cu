@@ -110,5 +110,6 @@ extern "C" __attribute__((visibility("default"))) int moma_ema_multi(const void*
     ema_multi_kernel<<<(unsigned)n_chunks, kEmaThreads, 0, as_stream(stream)>>>(
         static_cast<const EmaChunk*>(dev_table), m, one_minus_m);
     MOMA_CUDA_LAUNCH_CHECK("ema_multi");
+    note_launches(1);
     return MOMA_OK;
 }

@@ -147,6 +147,7 @@ extern "C" __attribute__((visibility("default"))) int moma_l2norm_fwd(const floa
     const unsigned grid = (unsigned)((rows + kNormWarps - 1) / kNormWarps);
     l2norm_kernel<false><<<grid, kNormWarps * 32, 0, as_stream(stream)>>>(x, nullptr, y, rows, D, eps);
     MOMA_CUDA_LAUNCH_CHECK("l2norm_fwd");
+    note_launches(1);
     return MOMA_OK;
 }
 
@@ -158,6 +159,7 @@ extern "C" __attribute__((visibility("default"))) int moma_l2norm_bwd(const floa
     const unsigned grid = (unsigned)((rows + kNormWarps - 1) / kNormWarps);
     l2norm_kernel<true><<<grid, kNormWarps * 32, 0, as_stream(stream)>>>(x, grad_y, grad_x, rows, D, eps);
     MOMA_CUDA_LAUNCH_CHECK("l2norm_bwd");
+    note_launches(1);
     return MOMA_OK;
 }
 
@@ -183,6 +185,7 @@ extern "C" __attribute__((visibility("default"))) int moma_enqueue(const float* 
         keys, n, D, queue_f32, static_cast<__nv_bfloat16*>(queue_bf16), K, index, index_dev,
         shard_rank, shard_world, normalize, eps);
     MOMA_CUDA_LAUNCH_CHECK("enqueue");
+    note_launches(1);
     return MOMA_OK;
 }
 
@@ -192,6 +195,7 @@ extern "C" __attribute__((visibility("default"))) int moma_enqueue_ids(int64_t n
     if (n == 0) return MOMA_OK;
     enqueue_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(n, index, index_dev, K, out_ids);
     MOMA_CUDA_LAUNCH_CHECK("enqueue_ids");
+    note_launches(1);
     return MOMA_OK;
 }
 
@@ -199,6 +203,7 @@ extern "C" __attribute__((visibility("default"))) int moma_pointer_advance(int64
     MOMA_REQUIRE(index_dev && n >= 0 && K > 0, MOMA_ERR_INVALID, "pointer_advance: bad arguments");
     pointer_advance_kernel<<<1, 32, 0, as_stream(stream)>>>(index_dev, n, K);
     MOMA_CUDA_LAUNCH_CHECK("pointer_advance");
+    note_launches(1);
     return MOMA_OK;
 }
 
@@ -214,5 +219,6 @@ extern "C" __attribute__((visibility("default"))) int moma_cast_bf16(const float
     cast_bf16_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
         src, static_cast<__nv_bfloat16*>(dst_bf16), nvec, numel);
     MOMA_CUDA_LAUNCH_CHECK("cast_bf16");
+    note_launches(1);
     return MOMA_OK;
 }

@@ -357,6 +357,7 @@ static int partial_f32(const float* q, const float* queue, int64_t B, int64_t D,
         nce_partial_f32_kernel<BN><<<grid, kSimtThreads, smem, st>>>(q, queue, (int)B, (int)D, K, inv_T, n_splits, pm, pl, pmm, pO);
     }
     MOMA_CUDA_LAUNCH_CHECK("nce_partial(f32)");
+    note_launches(1);
     return MOMA_OK;
 }
 
@@ -411,6 +412,7 @@ extern "C" __attribute__((visibility("default"))) int moma_nce_combine(const flo
         part_m, part_l, part_mmax, part_O, n_parts, q_f32, kpos_f32, (int)B, (int)D, inv_T,
         loss_rows, dq_unit, pos_is_max, max_logit);
     MOMA_CUDA_LAUNCH_CHECK("nce_combine");
+    note_launches(1);
     return MOMA_OK;
 }
 
@@ -423,6 +425,7 @@ extern "C" __attribute__((visibility("default"))) int moma_nce_merge(
     nce_merge_kernel<<<(unsigned)B, 128, 0, as_stream(stream)>>>(part_m, part_l, part_mmax, part_O, n_parts,
                                                                 (int)B, (int)D, out_m, out_l, out_mmax, out_O);
     MOMA_CUDA_LAUNCH_CHECK("nce_merge");
+    note_launches(1);
     return MOMA_OK;
 }
 
@@ -444,6 +447,7 @@ extern "C" __attribute__((visibility("default"))) int moma_nce_logits(const void
         return fail(MOMA_ERR_INVALID, "nce_logits: unknown dtype %d", dtype);
     }
     MOMA_CUDA_LAUNCH_CHECK("nce_logits");
+    note_launches(2);
     return MOMA_OK;
 }
 
@@ -452,5 +456,6 @@ extern "C" __attribute__((visibility("default"))) int moma_nce_logits_qk(const f
     MOMA_REQUIRE(B > 0 && D > 0 && q && kpos && out && T != 0.f, MOMA_ERR_INVALID, "nce_logits_qk: bad arguments");
     nce_pos_kernel<float><<<(unsigned)((B + 3) / 4), 128, 0, as_stream(stream)>>>(q, kpos, (int)B, (int)D, T, out, 1);
     MOMA_CUDA_LAUNCH_CHECK("nce_logits_qk");
+    note_launches(1);
     return MOMA_OK;
 }

@@ -552,6 +552,7 @@ static int launch(const void* q, const void* queue, int64_t B, int64_t K_local, 
     nce_tc_kernel<D, NQ, BN><<<grid, C::THREADS, C::SMEM_TOTAL, st>>>(mq, mk, (int)B, (long long)K_local, scale_log2,
                                                                      n_splits, pm, pl, pmm, pO, dbg);
     MOMA_CUDA_LAUNCH_CHECK("nce_partial(bf16/tcgen05)");
+    note_launches(1);
     return MOMA_OK;
 }
 

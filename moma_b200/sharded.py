@@ -1,0 +1,159 @@
+"""K-sharded momentum memory bank across the ranks of one node.
+
+The reference replicates the whole ``[K, D]`` queue on every rank and each rank scans all K rows
+(MoMA/mem_moco.py:97-99 with learning/contrast_trainer.py:124).  Here the queue rows are sharded
+*cyclically*: global row ``g`` lives on rank ``g % W`` at local slot ``g // W`` (K % W == 0).  The
+global ids are exactly the reference's ``(index + j) % K`` (bit-exact), and because a step's ids are
+consecutive every rank receives ``n / W`` of the new rows (balanced enqueue).
+
+Per step (all latency-bound, tiny payloads):
+  1. all-gather of the queries ``[B_local, D]`` -> ``[n, D]`` (bf16 in bf16 mode) so each rank scores
+     all ``n`` global queries against its ``K / W`` rows -- same FLOPs per rank as one GPU at B_local;
+  2. fused partial pass over the local shard (+ local merge of the split partials);
+  3. exchange: rank j receives the W partials ``(m, l, mmax, O)`` of its own ``B_local`` queries
+     (all-to-all on NCCL; all-gather + slice where the backend lacks all-to-all, e.g. gloo on CPU tests);
+  4. combine with the positive column (local q, k) -> loss rows, d loss/d q, top-1 flags;
+  5. enqueue: every rank writes the rows it owns out of the all-gathered keys (the caller's
+     ``_global_gather``, learning/contrast_trainer.py:83-88).
+``state_dict()['memory']`` still presents the full ``[K, D]`` fp32 queue (gathered), see ``memory``.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from . import ops
+from .lazy_logits import LazyLogits
+from .mem_moco import BaseMoCo, _stale_after_enqueue
+
+
+def cyclic_shard(full: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    """Rows g with g % world == rank, in slot order g // world."""
+    return full[rank::world].contiguous()
+
+
+def cyclic_unshard(shards) -> torch.Tensor:
+    world = len(shards)
+    rows = shards[0].shape[0]
+    out = shards[0].new_empty((rows * world,) + tuple(shards[0].shape[1:]))
+    for r, s in enumerate(shards):
+        out[r::world] = s
+    return out
+
+
+class ShardedMoCo(BaseMoCo):
+    """Drop-in for MoCo (same ctor / forward signature) with the queue sharded by K over the
+    default process group."""
+
+    is_sharded = True
+
+    def __init__(self, n_dim, K=65536, T=0.07, mem_name='memory', group=None):
+        super().__init__(K, T)
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if K % self.world != 0:
+            raise ValueError(f"sharded queue needs K % world == 0 (K={K}, world={self.world})")
+        # identical RNG draw to the reference on every rank (same seed -> same queue), then keep our rows
+        full = F.normalize(torch.randn(K, n_dim))
+        self.n_dim = n_dim
+        self.register_buffer("memory_shard", cyclic_shard(full, self.rank, self.world), persistent=False)
+
+    # ---- full-queue views (collective: call on every rank) ------------------------------------
+    def gather_full(self) -> torch.Tensor:
+        return cyclic_unshard(list(self._all_gather(self.memory_shard).unbind(0)))
+
+    def _all_gather(self, x: torch.Tensor) -> torch.Tensor:
+        """[W, *x.shape]; the output is laid out as the dim-0 concatenation (accepted by NCCL and gloo)."""
+        x = x.contiguous()
+        out = torch.empty((self.world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(out, x, group=self.group)
+        return out.view((self.world,) + tuple(x.shape))
+
+    @property
+    def memory(self) -> torch.Tensor:
+        """Full [K, D] fp32 queue in the reference's row order (collective)."""
+        return self.gather_full()
+
+    def set_full(self, full: torch.Tensor) -> None:
+        self.memory_shard.copy_(cyclic_shard(full.to(self.memory_shard.device), self.rank, self.world))
+
+    def broadcast_from_rank0(self) -> None:
+        """ContrastTrainer.broadcast_memory for the sharded queue (reference :71-81)."""
+        full = self.gather_full()
+        # rank 0's view of every shard is authoritative only for its own rows; rebuild from rank 0's RNG draw
+        dist.broadcast(full, 0, group=self.group)
+        self.set_full(full)
+
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        super()._save_to_state_dict(destination, prefix, keep_vars)
+        destination[prefix + "memory"] = self.gather_full()
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        key = prefix + "memory"
+        if key in state_dict:
+            self.set_full(state_dict.pop(key))
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+    # ---- exchange of the per-rank partials ------------------------------------------------------
+    def _exchange(self, packed: torch.Tensor) -> torch.Tensor:
+        """packed [W(dst), B_local, D + 3] -> [W(src), B_local, D + 3] for this rank's queries."""
+        backend = dist.get_backend(self.group)
+        out = torch.empty_like(packed)
+        if backend == "nccl":
+            dist.all_to_all_single(out, packed, group=self.group)
+            return out
+        return self._all_gather(packed)[:, self.rank].contiguous()
+
+    def forward(self, q, k, all_k=None):
+        bsz, D = q.shape
+        W = self.world
+        k = k.detach()
+        labels = self._labels(bsz, q.device)
+        precision = ops.get_precision()
+        use_bf16 = precision == "bf16" and ops.bf16_supported(D)
+        shadow = self._shadow_of(self.memory_shard) if use_bf16 else None
+        inv_T = 1.0 / self.T
+
+        q_op, dtype, q32, k32 = ops.nce_operands(q, k, "bf16" if use_bf16 else "fp32")
+        # 1. all-gather the queries (every rank must contribute the same B_local)
+        all_q = torch.empty((W * bsz, D), dtype=q_op.dtype, device=q.device)
+        dist.all_gather_into_tensor(all_q, q_op.contiguous(), group=self.group)
+        # 2. local pass over this rank's K / W rows for all n queries, then fold the splits
+        queue = shadow if use_bf16 else self.memory_shard
+        stats, Opart = ops.nce_partial(all_q, queue, inv_T, dtype)
+        stats, Opart = ops.nce_merge(stats, Opart)                  # [3, 1, n], [1, n, D]
+        # 3. exchange: pack (O | m | l | mmax) per row, route rows to their owner rank
+        packed = torch.cat([Opart[0], stats[:, 0].t()], dim=1).view(W, bsz, D + 3)
+        recv = self._exchange(packed)                               # [W(src), bsz, D + 3]
+        O_all = recv[:, :, :D].contiguous()
+        st_all = recv[:, :, D:].permute(2, 0, 1).contiguous()       # [3, W, bsz]
+        # 4. combine with the positive column
+        rows, dq_unit, pim, mx = ops.nce_combine(st_all, O_all, q32, k32, inv_T)
+        if q.requires_grad and torch.is_grad_enabled():
+            rows = _RowsWithGrad.apply(q, rows, dq_unit)
+        shape = (bsz, self.K + 1) if bsz != 1 else (self.K + 1,)
+        logits = LazyLogits(shape, q.device, rows, pim, lambda: mx, labels, _stale_after_enqueue)
+        # 5. enqueue the rows this rank owns
+        all_k = all_k if all_k is not None else k
+        with torch.no_grad():
+            if all_k.shape[0] > self.K:
+                raise RuntimeError("enqueue of more rows than K (duplicate ids)")
+            ops.enqueue(all_k, self.memory_shard, shadow if use_bf16 else self._shadow_of(self.memory_shard, create=False),
+                        self.K, self.index, rank=self.rank, world=W)
+        self._update_pointer(all_k.size(0))
+        return logits, labels
+
+
+class _RowsWithGrad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, rows, dq_unit):
+        ctx.save_for_backward(dq_unit)
+        ctx.q_dtype = q.dtype
+        return rows.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        (dq_unit,) = ctx.saved_tensors
+        return (g.unsqueeze(1) * dq_unit).to(ctx.q_dtype), None, None
