@@ -175,6 +175,9 @@ def run_ours(args, cfg, rank, world, local_rank):
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
     lib = _lib.load()
+    # everything runs on one side stream from the first call on (graph capture needs a non-default
+    # stream, and autograd binds gradient accumulation to the stream a leaf was first used on)
+    torch.cuda.set_stream(torch.cuda.Stream(device))
     cs = CriterionStep(cfg, rank, world, device)
     B, D, K = cfg["B"], cfg["D"], cfg["K"]
     peaks = {}
@@ -215,47 +218,68 @@ def run_ours(args, cfg, rank, world, local_rank):
         cs.step()
     torch.cuda.synchronize()
 
-    # ---- per-kernel events for the roofline (nce partial / ema), collected during the timed steps
-    prof = {"nce": [], "ema": []}
-    orig_partial, orig_ema_run = ops.nce_partial, ops.EmaPlan.run
-
-    def partial_hook(*a, **k):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); out = orig_partial(*a, **k); e1.record()
-        prof["nce"].append((e0, e1))
-        return out
-
-    def ema_hook(self, m):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); orig_ema_run(self, m); e1.record()
-        if self.elements > 1_000_000:
-            prof["ema"].append((e0, e1))
-
-    ops.nce_partial, ops.EmaPlan.run = partial_hook, ema_hook
-
     sampler = ClockSampler(local_rank)
     sampler.start()
+    # ---- eager module API (what the unchanged helper/loops_moma.py drives)
+    eager_ms = timed(cs.step, args.steps)
+
+    # ---- the same step captured once as a CUDA graph and replayed (no Python between kernels)
+    from moma_b200.graphed import GraphedStep
+    rows_per_step = B * world
     lib.moma_debug_launch_count(1)
-    total_ms = timed(cs.step, args.steps)
-    launches = int(lib.moma_debug_launch_count(1))
+    graphed = GraphedStep(cs.step, contrast=cs.contrast, rows_per_step=rows_per_step, warmup=3)
+    launches_per_step = int(lib.moma_debug_launch_count(1)) // 4       # 3 warm-up calls + 1 captured call
+    for _ in range(3):
+        graphed.replay()
+    total_ms = timed(graphed.replay, args.steps)
+    launches = launches_per_step * args.steps
+
+    # ---- end to end: host (pinned) inputs -> static device buffers, replay, host read of the loss
+    def step_e2e():
+        with torch.no_grad():
+            cs.feat_s.copy_(cs.host_s, non_blocking=True)
+            cs.feat_t.copy_(cs.host_t, non_blocking=True)
+        return float(graphed.replay().item())
+
+    for _ in range(3):
+        step_e2e()
+    e2e_ms = timed(step_e2e, args.steps)
     sampler.stop_flag = True
     sampler.join(timeout=1)
-    nce_us = 1e3 * sum(a.elapsed_time(b) for a, b in prof["nce"]) / max(len(prof["nce"]), 1)
-    ema_us = 1e3 * sum(a.elapsed_time(b) for a, b in prof["ema"]) / max(len(prof["ema"]), 1)
-    ops.nce_partial, ops.EmaPlan.run = orig_partial, orig_ema_run
 
-    # ---- end to end: host inputs, H2D + D2H inside the timed region
-    for _ in range(3):
-        cs.step_e2e()
-    e2e_ms = timed(cs.step_e2e, args.steps)
+    # ---- per-kernel CUDA-event timing for the rooflines: cold L2 (flush first; the flush also hides
+    #      the launch gap, so e0 -> e1 brackets the kernel alone), median of 20 launches
+    def kernel_us(launch):
+        ts = []
+        for _ in range(20):
+            if flush is not None:
+                flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); launch(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    from moma_b200._lib import BF16
+    plan = ops._EMA_PLANS[ops.plan_key([p.detach() for p in cs.student], [p.detach() for p in cs.teacher])]
+    ema_us = kernel_us(lambda: plan.run(ALPHA))
+    n_q = B * world
+    q_bf = torch.randn(n_q, D, device=device).to(torch.bfloat16)
+    shadow = cs.contrast._shadow_of(cs.contrast.memory_shard if world > 1 else cs.contrast.memory)
+    n_splits = ops.nce_num_splits(n_q, D, shadow.shape[0], BF16)
+    st_buf = torch.empty((3, n_splits, n_q), device=device)
+    o_buf = torch.empty((n_splits, n_q, D), device=device)
+    nce_us = kernel_us(lambda: _lib.check(lib.moma_nce_partial(
+        q_bf.data_ptr(), shadow.data_ptr(), n_q, D, shadow.shape[0], 1.0 / T_NCE, BF16, n_splits, st_buf[0].data_ptr(),
+        st_buf[1].data_ptr(), st_buf[2].data_ptr(), o_buf.data_ptr(), torch.cuda.current_stream().cuda_stream)))
 
     ms_per_step = total_ms / args.steps
     value = B * world / (ms_per_step * 1e-3)
     e2e_value = B * world / (e2e_ms / args.steps * 1e-3)
 
     # ---- rooflines (algorithmic work per launch)
-    n_q = B * world                                   # queries scored per rank (all-gathered)
-    k_local = K // world
+    k_local = K // world                              # n_q = B * world queries scored per rank (all-gathered)
     nce_flop = 4.0 * n_q * k_local * D                # S = Q.Queue^T and P.Queue, 2 FLOP/MAC each
     ema_bytes = 12.0 * cs.ema_elems                   # read ema, read src, write ema (fp32)
     tf_peak = peaks.get("bf16_tflops_sustained", 1421.9)
@@ -282,9 +306,13 @@ def run_ours(args, cfg, rank, world, local_rank):
                    "l2": "no flush" if args.no_flush else "L2 flushed (256 MiB write) before every step; per-step CUDA events summed",
                    "timed_region": "EMA + heads + 3x attention + fused InfoNCE/CE fwd+bwd + enqueue (criterion step, L1)"},
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": cs.h2d_bytes, "d2h_bytes_per_step": 4,
-                "ms_per_step": e2e_ms / args.steps},
+                "ms_per_step": e2e_ms / args.steps,
+                "path": "pinned host features -> static device buffers, graph replay, loss.item()"},
         "gpu_launches": launches,
-        "gpu_launches_per_step": launches / args.steps,
+        "gpu_launches_per_step": launches_per_step,
+        "eager": {"ms_per_step": eager_ms / args.steps, "value": B * world / (eager_ms / args.steps * 1e-3),
+                  "note": "same step through the eager module API (Python between kernels)"},
+        "execution": "whole criterion step (fwd+bwd) captured once as a CUDA graph and replayed",
         "roofline": dominant, "roofline_other": other,
         "clocks": sampler.summary(),
     }

@@ -14,52 +14,83 @@ namespace moma {
 
 // ------------------------------------------------------------------ generic SGEMM
 // C[m, n] = sum_k A(m,k) * B(n,k) (+ bias[n]);  A(m,k) = A[m*a_rs + k*a_cs], same for B.
-// 64x64x16 tiles, 256 threads, 4x4 micro-tile per thread.
+// The GEMMs of this path are tiny (M, N, K in the hundreds) and latency-bound, so the kernel is
+// built for few dependent phases and many CTAs: 32x32 output tile per 128-thread CTA, the whole
+// K strip (up to 128) staged in shared memory in ONE load phase, 128-bit shared-memory reads.
+constexpr int kGM = 32, kGN = 32, kGK = 128, kGLd = kGK + 4, kGThreads = 128;
+
+template <bool KCONTIG>
+__device__ __forceinline__ void load_strip(float* dst, const float* __restrict__ src, int64_t rs, int64_t cs,
+                                           int r0, int R, int k0, int K, bool vec_ok) {
+    const int tid = threadIdx.x;
+    if (KCONTIG) {
+        // consecutive lanes walk along k (contiguous): float4 when aligned
+#pragma unroll
+        for (int i = 0; i < (32 * kGK / 4) / kGThreads; ++i) {
+            const int idx = tid + i * kGThreads;
+            const int r = idx >> 5, v = idx & 31;
+            const int k = k0 + 4 * v;
+            float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r0 + r < R) {
+                const float* p = src + (int64_t)(r0 + r) * rs + k;
+                if (vec_ok && k + 3 < K) val = *reinterpret_cast<const float4*>(p);
+                else {
+                    if (k < K) val.x = p[0];
+                    if (k + 1 < K) val.y = p[1];
+                    if (k + 2 < K) val.z = p[2];
+                    if (k + 3 < K) val.w = p[3];
+                }
+            }
+            *reinterpret_cast<float4*>(dst + r * kGLd + 4 * v) = val;
+        }
+    } else {
+        // consecutive lanes walk along the row index (contiguous in memory), k strided by cs
+#pragma unroll 8
+        for (int i = 0; i < (32 * kGK) / kGThreads; ++i) {
+            const int idx = tid + i * kGThreads;
+            const int r = idx & 31, k = idx >> 5;
+            dst[r * kGLd + k] = (r0 + r < R && k0 + k < K) ? src[(int64_t)(k0 + k) * cs + (r0 + r)] : 0.f;
+        }
+    }
+}
+
 template <bool A_KCONTIG, bool B_KCONTIG>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kGThreads)
 sgemm_kernel(const float* __restrict__ A, int64_t a_rs, int64_t a_cs, const float* __restrict__ Bm,
              int64_t b_rs, int64_t b_cs, const float* __restrict__ bias, float* __restrict__ Cm,
-             int64_t ldc, int M, int N, int K) {
-    __shared__ float As[16][64 + 1];
-    __shared__ float Bs[16][64 + 1];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-    float acc[4][4] = {};
-    for (int k0 = 0; k0 < K; k0 += 16) {
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const int i = tid + it * 256;
-            {
-                const int r = A_KCONTIG ? (i >> 4) : (i & 63);
-                const int k = A_KCONTIG ? (i & 15) : (i >> 6);
-                As[k][r] = (m0 + r < M && k0 + k < K) ? A[(int64_t)(m0 + r) * a_rs + (int64_t)(k0 + k) * a_cs] : 0.f;
-            }
-            {
-                const int r = B_KCONTIG ? (i >> 4) : (i & 63);
-                const int k = B_KCONTIG ? (i & 15) : (i >> 6);
-                Bs[k][r] = (n0 + r < N && k0 + k < K) ? Bm[(int64_t)(n0 + r) * b_rs + (int64_t)(k0 + k) * b_cs] : 0.f;
-            }
-        }
+             int64_t ldc, int M, int N, int K, int a_vec, int b_vec) {
+    __shared__ __align__(16) float As[kGM * kGLd];
+    __shared__ __align__(16) float Bs[kGN * kGLd];
+    const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+    const int m0 = blockIdx.y * kGM, n0 = blockIdx.x * kGN;
+    float acc[2][4] = {};
+    for (int k0 = 0; k0 < K; k0 += kGK) {
+        if (k0 > 0) __syncthreads();
+        load_strip<A_KCONTIG>(As, A, a_rs, a_cs, m0, M, k0, K, a_vec != 0);
+        load_strip<B_KCONTIG>(Bs, Bm, b_rs, b_cs, n0, N, k0, K, b_vec != 0);
         __syncthreads();
+        const int kend = min(kGK, K - k0);
+#pragma unroll 4
+        for (int k = 0; k < kend; k += 4) {
+            float4 a[2], b[4];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            float a[4], b[4];
+            for (int i = 0; i < 2; ++i) a[i] = *reinterpret_cast<const float4*>(As + (ty + 16 * i) * kGLd + k);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { a[i] = As[k][ty + 16 * i]; b[i] = Bs[k][tx + 16 * i]; }
+            for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4*>(Bs + (tx + 8 * j) * kGLd + k);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 2; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+                for (int j = 0; j < 4; ++j)
+                    acc[i][j] += a[i].x * b[j].x + a[i].y * b[j].y + a[i].z * b[j].z + a[i].w * b[j].w;
         }
-        __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 2; ++i) {
         const int r = m0 + ty + 16 * i;
         if (r >= M) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int c = n0 + tx + 16 * j;
+            const int c = n0 + tx + 8 * j;
             if (c < N) Cm[(int64_t)r * ldc + c] = acc[i][j] + (bias ? bias[c] : 0.f);
         }
     }
@@ -68,12 +99,13 @@ sgemm_kernel(const float* __restrict__ A, int64_t a_rs, int64_t a_cs, const floa
 static void sgemm(const float* A, int64_t a_rs, int64_t a_cs, const float* Bm, int64_t b_rs,
                   int64_t b_cs, const float* bias, float* Cm, int64_t ldc, int M, int N, int K,
                   cudaStream_t st) {
-    const dim3 grid((N + 63) / 64, (M + 63) / 64);
+    const dim3 grid((N + kGN - 1) / kGN, (M + kGM - 1) / kGM);
     const bool ak = (a_cs == 1), bk = (b_cs == 1);
-    if (ak && bk) sgemm_kernel<true, true><<<grid, 256, 0, st>>>(A, a_rs, a_cs, Bm, b_rs, b_cs, bias, Cm, ldc, M, N, K);
-    else if (ak && !bk) sgemm_kernel<true, false><<<grid, 256, 0, st>>>(A, a_rs, a_cs, Bm, b_rs, b_cs, bias, Cm, ldc, M, N, K);
-    else if (!ak && bk) sgemm_kernel<false, true><<<grid, 256, 0, st>>>(A, a_rs, a_cs, Bm, b_rs, b_cs, bias, Cm, ldc, M, N, K);
-    else sgemm_kernel<false, false><<<grid, 256, 0, st>>>(A, a_rs, a_cs, Bm, b_rs, b_cs, bias, Cm, ldc, M, N, K);
+    const int av = ak && (a_rs % 4 == 0) && aligned16(A), bv = bk && (b_rs % 4 == 0) && aligned16(Bm);
+    if (ak && bk) sgemm_kernel<true, true><<<grid, kGThreads, 0, st>>>(A, a_rs, a_cs, Bm, b_rs, b_cs, bias, Cm, ldc, M, N, K, av, bv);
+    else if (ak && !bk) sgemm_kernel<true, false><<<grid, kGThreads, 0, st>>>(A, a_rs, a_cs, Bm, b_rs, b_cs, bias, Cm, ldc, M, N, K, av, bv);
+    else if (!ak && bk) sgemm_kernel<false, true><<<grid, kGThreads, 0, st>>>(A, a_rs, a_cs, Bm, b_rs, b_cs, bias, Cm, ldc, M, N, K, av, bv);
+    else sgemm_kernel<false, false><<<grid, kGThreads, 0, st>>>(A, a_rs, a_cs, Bm, b_rs, b_cs, bias, Cm, ldc, M, N, K, av, bv);
 }
 
 // column sums: out[c] = sum_r X[r, c]   (bias gradients)
@@ -96,16 +128,18 @@ colsum_kernel(const float* __restrict__ X, int rows, int cols, float* __restrict
 }
 
 // ------------------------------------------------------------------ fused attention core
-// Tiles: 32 "row" tokens per CTA (8 per warp, 4 warps), 64 "column" tokens per step.
+// Tiles: 32 "row" tokens per CTA (8 per warp, 4 warps) against KT "column" tokens per step.  KT is as
+// wide as shared memory allows (256 for head_dim <= 32) so that at the path's sizes (N = 256..1024)
+// a CTA goes through 1-4 load phases instead of N/64: these kernels are latency-bound.
 constexpr int kAR = 32;    // rows per CTA
-constexpr int kAC = 64;    // columns per inner tile
 constexpr int kAThreads = 128;
-constexpr int kLdP = kAC + 4;
 
 template <int HD> struct AttnCfg {
     static constexpr int LD = HD + 4;                       // padded smem row (floats)
     static constexpr int CPL = HD >= 32 ? HD / 32 : 1;      // output columns per lane
     static constexpr int RPL = HD >= 32 ? 8 : HD / 4;       // output rows per lane (32/HD row groups)
+    static constexpr int KT_FWD = HD <= 32 ? 256 : (HD == 64 ? 128 : 64);   // column tile, forward
+    static constexpr int KT_BWD = HD <= 32 ? 128 : 64;                      // column tile, backward (2 score tiles live)
     __device__ static int roff(int lane) { return HD >= 32 ? 0 : (lane / HD) * RPL; }
     __device__ static int cbase(int lane) { return HD >= 32 ? lane : (lane % HD); }
 };
@@ -123,36 +157,40 @@ __device__ __forceinline__ void load_rows(float* dst, const float* __restrict__ 
     }
 }
 
-// s[r][cc] = sum_d a[warp*8 + r][d] * b[lane + 32*cc][d]
-template <int HD>
+// s[r][cc] = sum_d a[warp*8 + r][d] * b[lane + 32*cc][d],  cc < KT/32
+template <int HD, int KT>
 __device__ __forceinline__ void dot_tile(const float* a_s, const float* b_s, int warp, int lane,
-                                         float (&s)[8][2]) {
-    constexpr int LD = HD + 4;
+                                         float (&s)[8][KT / 32]) {
+    constexpr int LD = HD + 4, CC = KT / 32;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) { s[r][0] = 0.f; s[r][1] = 0.f; }
-#pragma unroll 4
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int cc = 0; cc < CC; ++cc) s[r][cc] = 0.f;
+#pragma unroll 2
     for (int v = 0; v < HD / 4; ++v) {
-        const float4 b0 = *reinterpret_cast<const float4*>(b_s + lane * LD + 4 * v);
-        const float4 b1 = *reinterpret_cast<const float4*>(b_s + (lane + 32) * LD + 4 * v);
+        float4 b[CC];
+#pragma unroll
+        for (int cc = 0; cc < CC; ++cc) b[cc] = *reinterpret_cast<const float4*>(b_s + (lane + 32 * cc) * LD + 4 * v);
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             const float4 a = *reinterpret_cast<const float4*>(a_s + (warp * 8 + r) * LD + 4 * v);
-            s[r][0] += a.x * b0.x + a.y * b0.y + a.z * b0.z + a.w * b0.w;
-            s[r][1] += a.x * b1.x + a.y * b1.y + a.z * b1.z + a.w * b1.w;
+#pragma unroll
+            for (int cc = 0; cc < CC; ++cc)
+                s[r][cc] += a.x * b[cc].x + a.y * b[cc].y + a.z * b[cc].z + a.w * b[cc].w;
         }
     }
 }
 
-// acc[r][c] += sum_j p[row(r)][j] * v[j][col(c)],  j over the 64-column tile
-template <int HD>
+// acc[r][c] += sum_j p[row(r)][j] * v[j][col(c)],  j over the KT-column tile
+template <int HD, int KT>
 __device__ __forceinline__ void acc_tile(const float* p_s, const float* v_s, int warp, int lane,
                                          float (&acc)[AttnCfg<HD>::RPL][AttnCfg<HD>::CPL]) {
     using Cfg = AttnCfg<HD>;
-    constexpr int LD = Cfg::LD;
+    constexpr int LD = Cfg::LD, LDP = KT + 4;
     const int rbase = warp * 8 + Cfg::roff(lane);
     const int cbase = Cfg::cbase(lane);
 #pragma unroll 2
-    for (int j = 0; j < kAC; j += 4) {
+    for (int j = 0; j < KT; j += 4) {
         float vv[4][Cfg::CPL];
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj)
@@ -160,7 +198,7 @@ __device__ __forceinline__ void acc_tile(const float* p_s, const float* v_s, int
             for (int c = 0; c < Cfg::CPL; ++c) vv[jj][c] = v_s[(j + jj) * LD + cbase + 32 * c];
 #pragma unroll
         for (int r = 0; r < Cfg::RPL; ++r) {
-            const float4 p = *reinterpret_cast<const float4*>(p_s + (rbase + r) * kLdP + j);
+            const float4 p = *reinterpret_cast<const float4*>(p_s + (rbase + r) * LDP + j);
 #pragma unroll
             for (int c = 0; c < Cfg::CPL; ++c)
                 acc[r][c] += p.x * vv[0][c] + p.y * vv[1][c] + p.z * vv[2][c] + p.w * vv[3][c];
@@ -174,11 +212,12 @@ __global__ void __launch_bounds__(kAThreads)
 attn_fwd_kernel(const float* __restrict__ qkv, int N, int C, float scale, float* __restrict__ o,
                 float* __restrict__ lse) {
     using Cfg = AttnCfg<HD>;
+    constexpr int KT = Cfg::KT_FWD, CC = KT / 32, LDP = KT + 4;
     extern __shared__ __align__(16) float sm[];
     float* q_s = sm;                         // [32][LD]
-    float* k_s = q_s + kAR * Cfg::LD;        // [64][LD]
-    float* v_s = k_s + kAC * Cfg::LD;        // [64][LD]
-    float* p_s = v_s + kAC * Cfg::LD;        // [32][kLdP]
+    float* k_s = q_s + kAR * Cfg::LD;        // [KT][LD]
+    float* v_s = k_s + KT * Cfg::LD;         // [KT][LD]
+    float* p_s = v_s + KT * Cfg::LD;         // [32][LDP]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int h = blockIdx.y, i0 = blockIdx.x * kAR;
     const int64_t ldg = 3 * (int64_t)C;
@@ -191,43 +230,48 @@ attn_fwd_kernel(const float* __restrict__ qkv, int N, int C, float scale, float*
 #pragma unroll
     for (int r = 0; r < 8; ++r) { m_run[r] = -CUDART_INF_F; l_run[r] = 0.f; }
     float acc[Cfg::RPL][Cfg::CPL] = {};
+    const int roff = Cfg::roff(lane);
 
-    for (int j0 = 0; j0 < N; j0 += kAC) {
+    for (int j0 = 0; j0 < N; j0 += KT) {
+        if (j0 > 0) __syncthreads();
+        load_rows<HD>(k_s, kg, ldg, j0, KT, N);
+        load_rows<HD>(v_s, vg, ldg, j0, KT, N);
         __syncthreads();
-        load_rows<HD>(k_s, kg, ldg, j0, kAC, N);
-        load_rows<HD>(v_s, vg, ldg, j0, kAC, N);
-        __syncthreads();
-        float s[8][2];
-        dot_tile<HD>(q_s, k_s, warp, lane, s);
+        float s[8][CC];
+        dot_tile<HD, KT>(q_s, k_s, warp, lane, s);
         float corr[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            const float s0 = (j0 + lane < N) ? s[r][0] * scale : -CUDART_INF_F;
-            const float s1 = (j0 + lane + 32 < N) ? s[r][1] * scale : -CUDART_INF_F;
-            const float mx = warp_max(fmaxf(s0, s1));
+            float mx = -CUDART_INF_F;
+#pragma unroll
+            for (int cc = 0; cc < CC; ++cc) {
+                s[r][cc] = (j0 + lane + 32 * cc < N) ? s[r][cc] * scale : -CUDART_INF_F;
+                mx = fmaxf(mx, s[r][cc]);
+            }
+            mx = warp_max(mx);
             const float m_new = fmaxf(m_run[r], mx);
             corr[r] = (m_run[r] == -CUDART_INF_F) ? 0.f : expf(m_run[r] - m_new);
-            const float p0 = (s0 == -CUDART_INF_F) ? 0.f : expf(s0 - m_new);
-            const float p1 = (s1 == -CUDART_INF_F) ? 0.f : expf(s1 - m_new);
-            p_s[(warp * 8 + r) * kLdP + lane] = p0;
-            p_s[(warp * 8 + r) * kLdP + lane + 32] = p1;
-            l_run[r] = l_run[r] * corr[r] + warp_sum(p0 + p1);
+            float sum = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < CC; ++cc) {
+                const float p = (s[r][cc] == -CUDART_INF_F) ? 0.f : expf(s[r][cc] - m_new);
+                p_s[(warp * 8 + r) * LDP + lane + 32 * cc] = p;
+                sum += p;
+            }
+            l_run[r] = l_run[r] * corr[r] + warp_sum(sum);
             m_run[r] = m_new;
         }
-        const int roff = Cfg::roff(lane);
 #pragma unroll
         for (int r = 0; r < Cfg::RPL; ++r) {
-            // corr is warp-uniform per row; pick this lane's rows
-            float cr = corr[0];
+            float cr = corr[0];                 // corr is warp-uniform per row; pick this lane's rows
 #pragma unroll
             for (int rr = 0; rr < 8; ++rr) cr = (rr == r + roff) ? corr[rr] : cr;
 #pragma unroll
             for (int c = 0; c < Cfg::CPL; ++c) acc[r][c] *= cr;
         }
         __syncwarp();
-        acc_tile<HD>(p_s, v_s, warp, lane, acc);
+        acc_tile<HD, KT>(p_s, v_s, warp, lane, acc);
     }
-    const int roff = Cfg::roff(lane);
     const int cbase = Cfg::cbase(lane);
 #pragma unroll
     for (int r = 0; r < Cfg::RPL; ++r) {
@@ -289,12 +333,13 @@ attn_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
                    const float* __restrict__ lse, const float* __restrict__ delta, int N, int C,
                    float scale, float* __restrict__ dqkv) {
     using Cfg = AttnCfg<HD>;
+    constexpr int KT = Cfg::KT_BWD, CC = KT / 32, LDP = KT + 4;
     extern __shared__ __align__(16) float sm[];
     float* q_s = sm;                          // [32][LD]
     float* do_s = q_s + kAR * Cfg::LD;        // [32][LD]
-    float* k_s = do_s + kAR * Cfg::LD;        // [64][LD]
-    float* v_s = k_s + kAC * Cfg::LD;         // [64][LD]
-    float* p_s = v_s + kAC * Cfg::LD;         // [32][kLdP]  (holds dS)
+    float* k_s = do_s + kAR * Cfg::LD;        // [KT][LD]
+    float* v_s = k_s + KT * Cfg::LD;          // [KT][LD]
+    float* p_s = v_s + KT * Cfg::LD;          // [32][LDP]  (holds dS)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int h = blockIdx.y, i0 = blockIdx.x * kAR;
     const int64_t ldg = 3 * (int64_t)C;
@@ -308,25 +353,25 @@ attn_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
         del_r[r] = row < N ? delta[(int64_t)h * N + row] : 0.f;
     }
     float acc[Cfg::RPL][Cfg::CPL] = {};
-    for (int j0 = 0; j0 < N; j0 += kAC) {
+    for (int j0 = 0; j0 < N; j0 += KT) {
+        if (j0 > 0) __syncthreads();
+        load_rows<HD>(k_s, qkv + C + h * HD, ldg, j0, KT, N);
+        load_rows<HD>(v_s, qkv + 2 * C + h * HD, ldg, j0, KT, N);
         __syncthreads();
-        load_rows<HD>(k_s, qkv + C + h * HD, ldg, j0, kAC, N);
-        load_rows<HD>(v_s, qkv + 2 * C + h * HD, ldg, j0, kAC, N);
-        __syncthreads();
-        float s[8][2], dp[8][2];
-        dot_tile<HD>(q_s, k_s, warp, lane, s);
-        dot_tile<HD>(do_s, v_s, warp, lane, dp);
+        float s[8][CC], dp[8][CC];
+        dot_tile<HD, KT>(q_s, k_s, warp, lane, s);
+        dot_tile<HD, KT>(do_s, v_s, warp, lane, dp);
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
+            for (int cc = 0; cc < CC; ++cc) {
                 const bool ok = (j0 + lane + 32 * cc < N);
                 const float p = ok ? expf(s[r][cc] * scale - lse_r[r]) : 0.f;
-                p_s[(warp * 8 + r) * kLdP + lane + 32 * cc] = p * (dp[r][cc] - del_r[r]);
+                p_s[(warp * 8 + r) * LDP + lane + 32 * cc] = p * (dp[r][cc] - del_r[r]);
             }
         }
         __syncwarp();
-        acc_tile<HD>(p_s, k_s, warp, lane, acc);
+        acc_tile<HD, KT>(p_s, k_s, warp, lane, acc);
     }
     const int roff = Cfg::roff(lane);
     const int cbase = Cfg::cbase(lane);
@@ -347,13 +392,14 @@ attn_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
                     const float* __restrict__ lse, const float* __restrict__ delta, int N, int C,
                     float scale, float* __restrict__ dqkv) {
     using Cfg = AttnCfg<HD>;
+    constexpr int KT = Cfg::KT_BWD, CC = KT / 32, LDP = KT + 4;
     extern __shared__ __align__(16) float sm[];
     float* k_s = sm;                           // [32][LD]  own keys
     float* v_s = k_s + kAR * Cfg::LD;          // [32][LD]  own values
-    float* q_s = v_s + kAR * Cfg::LD;          // [64][LD]  query tile
-    float* do_s = q_s + kAC * Cfg::LD;         // [64][LD]  dO tile
-    float* p_s = do_s + kAC * Cfg::LD;         // [32][kLdP]  P^T
-    float* ds_s = p_s + kAR * kLdP;            // [32][kLdP]  dS^T
+    float* q_s = v_s + kAR * Cfg::LD;          // [KT][LD]  query tile
+    float* do_s = q_s + KT * Cfg::LD;          // [KT][LD]  dO tile
+    float* p_s = do_s + KT * Cfg::LD;          // [32][LDP]  P^T
+    float* ds_s = p_s + kAR * LDP;             // [32][LDP]  dS^T
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int h = blockIdx.y, j0 = blockIdx.x * kAR;
     const int64_t ldg = 3 * (int64_t)C;
@@ -361,17 +407,17 @@ attn_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
     load_rows<HD>(v_s, qkv + 2 * C + h * HD, ldg, j0, kAR, N);
     float acc_k[Cfg::RPL][Cfg::CPL] = {};
     float acc_v[Cfg::RPL][Cfg::CPL] = {};
-    for (int i0 = 0; i0 < N; i0 += kAC) {
+    for (int i0 = 0; i0 < N; i0 += KT) {
+        if (i0 > 0) __syncthreads();
+        load_rows<HD>(q_s, qkv + h * HD, ldg, i0, KT, N);
+        load_rows<HD>(do_s, dO + h * HD, C, i0, KT, N);
         __syncthreads();
-        load_rows<HD>(q_s, qkv + h * HD, ldg, i0, kAC, N);
-        load_rows<HD>(do_s, dO + h * HD, C, i0, kAC, N);
-        __syncthreads();
-        float st[8][2], dpt[8][2];
-        dot_tile<HD>(k_s, q_s, warp, lane, st);      // st[r][cc] = k_j . q_i
-        dot_tile<HD>(v_s, do_s, warp, lane, dpt);    // dpt      = v_j . do_i
-        float lse_c[2], del_c[2];
+        float st[8][CC], dpt[8][CC];
+        dot_tile<HD, KT>(k_s, q_s, warp, lane, st);      // st[r][cc] = k_j . q_i
+        dot_tile<HD, KT>(v_s, do_s, warp, lane, dpt);    // dpt      = v_j . do_i
+        float lse_c[CC], del_c[CC];
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
+        for (int cc = 0; cc < CC; ++cc) {
             const int i = i0 + lane + 32 * cc;
             lse_c[cc] = i < N ? lse[(int64_t)h * N + i] : 0.f;
             del_c[cc] = i < N ? delta[(int64_t)h * N + i] : 0.f;
@@ -380,16 +426,16 @@ attn_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
         for (int r = 0; r < 8; ++r) {
             const bool rok = (j0 + warp * 8 + r < N);
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
+            for (int cc = 0; cc < CC; ++cc) {
                 const bool ok = rok && (i0 + lane + 32 * cc < N);
                 const float p = ok ? expf(st[r][cc] * scale - lse_c[cc]) : 0.f;
-                p_s[(warp * 8 + r) * kLdP + lane + 32 * cc] = p;
-                ds_s[(warp * 8 + r) * kLdP + lane + 32 * cc] = p * (dpt[r][cc] - del_c[cc]);
+                p_s[(warp * 8 + r) * LDP + lane + 32 * cc] = p;
+                ds_s[(warp * 8 + r) * LDP + lane + 32 * cc] = p * (dpt[r][cc] - del_c[cc]);
             }
         }
         __syncwarp();
-        acc_tile<HD>(p_s, do_s, warp, lane, acc_v);
-        acc_tile<HD>(ds_s, q_s, warp, lane, acc_k);
+        acc_tile<HD, KT>(p_s, do_s, warp, lane, acc_v);
+        acc_tile<HD, KT>(ds_s, q_s, warp, lane, acc_k);
     }
     const int roff = Cfg::roff(lane);
     const int cbase = Cfg::cbase(lane);
@@ -405,9 +451,18 @@ attn_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
     }
 }
 
-template <int HD> static size_t fwd_smem() { return (size_t)((kAR + 2 * kAC) * (HD + 4) + kAR * kLdP) * sizeof(float); }
-template <int HD> static size_t dq_smem() { return (size_t)((2 * kAR + 2 * kAC) * (HD + 4) + kAR * kLdP) * sizeof(float); }
-template <int HD> static size_t dkv_smem() { return (size_t)((2 * kAR + 2 * kAC) * (HD + 4) + 2 * kAR * kLdP) * sizeof(float); }
+template <int HD> static size_t fwd_smem() {
+    constexpr int KT = AttnCfg<HD>::KT_FWD;
+    return (size_t)((kAR + 2 * KT) * (HD + 4) + kAR * (KT + 4)) * sizeof(float);
+}
+template <int HD> static size_t dq_smem() {
+    constexpr int KT = AttnCfg<HD>::KT_BWD;
+    return (size_t)((2 * kAR + 2 * KT) * (HD + 4) + kAR * (KT + 4)) * sizeof(float);
+}
+template <int HD> static size_t dkv_smem() {
+    constexpr int KT = AttnCfg<HD>::KT_BWD;
+    return (size_t)((2 * kAR + 2 * KT) * (HD + 4) + 2 * kAR * (KT + 4)) * sizeof(float);
+}
 
 template <int HD>
 static void launch_fwd(const float* qkv, int N, int C, int H, float scale, float* o, float* lse, cudaStream_t st) {

@@ -168,110 +168,127 @@ nce_partial_f32_kernel(const float* __restrict__ q, const float* __restrict__ qu
     }
 }
 
-// ------------------------------------------------------------------ combine
-// One CTA of 128 threads per query row.
-__global__ void __launch_bounds__(128)
-nce_combine_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l,
-                   const float* __restrict__ part_mmax, const float* __restrict__ part_O,
-                   int n_parts, const float* __restrict__ q, const float* __restrict__ kpos, int B,
-                   int D, float inv_T, float* __restrict__ loss_rows, float* __restrict__ dq_unit,
-                   int32_t* __restrict__ pos_is_max, float* __restrict__ max_logit) {
-    __shared__ float red[4];
-    __shared__ float s_w[256];
-    const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float* qr = q + (int64_t)row * D;
-    const float* kr = kpos + (int64_t)row * D;
-    float dot = 0.f;
-    for (int d = tid; d < D; d += 128) dot += qr[d] * kr[d];
-    dot = warp_sum(dot);
-    if (lane == 0) red[warp] = dot;
-    __syncthreads();
-    const float pos = (red[0] + red[1] + red[2] + red[3]) * inv_T;
+// ------------------------------------------------------------------ combine / merge
+// One CTA of 128 threads per query row.  Reductions over the partials are spread over the
+// threads (max / weights / l through shuffles + shared memory); the O accumulation keeps one
+// column per thread with the loop over parts unrolled so the loads are in flight together.
+constexpr int kCombThreads = 128;
+constexpr int kCombChunk = 512;       // parts staged per pass
 
+__device__ __forceinline__ float block_max(float v, float* red) {
+    v = warp_max(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    v = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    __syncthreads();
+    return v;
+}
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    v = (red[0] + red[1]) + (red[2] + red[3]);
+    __syncthreads();
+    return v;
+}
+
+// kFinal: add the positive column and emit loss / dq / flags; otherwise emit one merged partial.
+template <bool kFinal>
+__global__ void __launch_bounds__(kCombThreads)
+nce_reduce_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l,
+                  const float* __restrict__ part_mmax, const float* __restrict__ part_O, int n_parts,
+                  const float* __restrict__ q, const float* __restrict__ kpos, int B, int D, float inv_T,
+                  float* __restrict__ out_a /* loss_rows | out_m */, float* __restrict__ out_O /* dq_unit | out_O */,
+                  int32_t* __restrict__ pos_is_max, float* __restrict__ out_b /* max_logit | out_l */,
+                  float* __restrict__ out_c /* - | out_mmax */) {
+    __shared__ float red[4];
+    __shared__ float s_w[kCombChunk];
+    const int row = blockIdx.x, tid = threadIdx.x;
+    const float* kr = kFinal ? kpos + (int64_t)row * D : nullptr;
+
+    float pos = 0.f;
+    if (kFinal) {
+        const float* qr = q + (int64_t)row * D;
+        float dot = 0.f;
+        for (int d = tid; d < D; d += kCombThreads) dot += qr[d] * kr[d];
+        pos = block_sum(dot, red) * inv_T;
+    }
     float mref = -CUDART_INF_F, mtrue = -CUDART_INF_F;
-    for (int s = 0; s < n_parts; ++s) {
+    for (int s = tid; s < n_parts; s += kCombThreads) {
         mref = fmaxf(mref, part_m[(int64_t)s * B + row]);
         mtrue = fmaxf(mtrue, part_mmax[(int64_t)s * B + row]);
     }
-    const float mstar = fmaxf(mref, pos);
-    const float wpos = expf(pos - mstar);
+    mref = block_max(mref, red);
+    mtrue = block_max(mtrue, red);
+    const float mstar = kFinal ? fmaxf(mref, pos) : mref;
+    const float wpos = kFinal ? expf(pos - mstar) : 0.f;
 
-    float l = wpos;
-    // D <= 128*4 handled with up to 4 columns per thread; larger D loops
-    for (int d0 = 0; d0 < D; d0 += 512) {
+    float l_part = 0.f;
+    // columns handled by this thread: tid + 128*c, c < 4 per pass (D <= 512 in one pass)
+    for (int d0 = 0; d0 < D; d0 += 4 * kCombThreads) {
         float o[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const int d = d0 + tid + 128 * c;
-            o[c] = (d < D) ? wpos * kr[d] : 0.f;
+            const int d = d0 + tid + kCombThreads * c;
+            o[c] = (kFinal && d < D) ? wpos * kr[d] : 0.f;
         }
-        for (int s0 = 0; s0 < n_parts; s0 += 256) {
-            const int cnt = min(256, n_parts - s0);
+        for (int s0 = 0; s0 < n_parts; s0 += kCombChunk) {
+            const int cnt = min(kCombChunk, n_parts - s0);
             __syncthreads();
-            for (int s = tid; s < cnt; s += 128) {
-                const float ms = part_m[(int64_t)(s0 + s) * B + row];
-                s_w[s] = (ms == -CUDART_INF_F) ? 0.f : expf(ms - mstar);
+            for (int s = tid; s < cnt; s += kCombThreads) {
+                const int64_t base = (int64_t)(s0 + s) * B + row;
+                const float ms = part_m[base];
+                const float w = (ms == -CUDART_INF_F) ? 0.f : expf(ms - mstar);
+                s_w[s] = w;
+                if (d0 == 0) l_part += w * part_l[base];
             }
             __syncthreads();
-            for (int s = 0; s < cnt; ++s) {
-                const float w = s_w[s];
-                const int64_t base = ((int64_t)(s0 + s) * B + row);
-                if (d0 == 0 && tid == 0) l += w * part_l[base];
-                const float* Os = part_O + base * D;
+            const float* Op = part_O + ((int64_t)s0 * B + row) * D;
+            const int64_t sstride = (int64_t)B * D;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int d = d0 + tid + 128 * c;
-                    if (d < D) o[c] += w * Os[d];
+            for (int c = 0; c < 4; ++c) {
+                const int d = d0 + tid + kCombThreads * c;
+                if (d < D) {
+                    float acc = o[c];
+                    int s = 0;
+                    for (; s + 8 <= cnt; s += 8) {
+                        float v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) v[u] = __ldg(Op + (int64_t)(s + u) * sstride + d);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) acc = fmaf(s_w[s + u], v[u], acc);
+                    }
+                    for (; s < cnt; ++s) acc = fmaf(s_w[s], __ldg(Op + (int64_t)s * sstride + d), acc);
+                    o[c] = acc;
                 }
             }
         }
+        float l = 0.f;
         if (d0 == 0) {
-            __syncthreads();
+            l = block_sum(l_part, red) + wpos;
             if (tid == 0) red[0] = l;
             __syncthreads();
-            l = red[0];
+            l_part = l;                  // every thread now holds the total
         }
+        l = l_part;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const int d = d0 + tid + 128 * c;
-            if (d < D) dq_unit[(int64_t)row * D + d] = (o[c] / l - kr[d]) * inv_T;
+            const int d = d0 + tid + kCombThreads * c;
+            if (d < D) {
+                if (kFinal) out_O[(int64_t)row * D + d] = (o[c] / l - kr[d]) * inv_T;
+                else out_O[(int64_t)row * D + d] = o[c];
+            }
         }
     }
     if (tid == 0) {
-        loss_rows[row] = logf(l) + mstar - pos;
-        pos_is_max[row] = (pos >= mtrue) ? 1 : 0;
-        if (max_logit) max_logit[row] = fmaxf(pos, mtrue);
-    }
-}
-
-// ------------------------------------------------------------------ merge (splits -> 1 partial)
-// Used by the K-sharded queue: each rank folds its local splits into one partial per query row
-// before the cross-rank exchange, so (D + 3) floats per row travel instead of n_splits times that.
-__global__ void __launch_bounds__(128)
-nce_merge_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l,
-                 const float* __restrict__ part_mmax, const float* __restrict__ part_O, int n_parts,
-                 int B, int D, float* __restrict__ out_m, float* __restrict__ out_l,
-                 float* __restrict__ out_mmax, float* __restrict__ out_O) {
-    const int row = blockIdx.x, tid = threadIdx.x;
-    float mref = -CUDART_INF_F, mtrue = -CUDART_INF_F;
-    for (int s = 0; s < n_parts; ++s) {
-        mref = fmaxf(mref, part_m[(int64_t)s * B + row]);
-        mtrue = fmaxf(mtrue, part_mmax[(int64_t)s * B + row]);
-    }
-    float l = 0.f;
-    for (int d0 = 0; d0 < D; d0 += 128) {
-        const int d = d0 + tid;
-        float o = 0.f;
-        for (int s = 0; s < n_parts; ++s) {
-            const int64_t base = (int64_t)s * B + row;
-            const float ms = part_m[base];
-            const float w = (ms == -CUDART_INF_F) ? 0.f : expf(ms - mref);
-            if (d0 == 0 && tid == 0) l += w * part_l[base];
-            if (d < D) o += w * part_O[base * D + d];
+        if (kFinal) {
+            out_a[row] = logf(l_part) + mstar - pos;
+            pos_is_max[row] = (pos >= mtrue) ? 1 : 0;
+            if (out_b) out_b[row] = fmaxf(pos, mtrue);
+        } else {
+            out_a[row] = mref; out_b[row] = l_part; out_c[row] = mtrue;
         }
-        if (d < D) out_O[(int64_t)row * D + d] = o;
     }
-    if (tid == 0) { out_m[row] = mref; out_l[row] = l; out_mmax[row] = mtrue; }
 }
 
 // ------------------------------------------------------------------ materialise
@@ -408,9 +425,9 @@ extern "C" __attribute__((visibility("default"))) int moma_nce_combine(const flo
     MOMA_REQUIRE(B > 0 && D > 0 && n_parts > 0, MOMA_ERR_INVALID, "nce_combine: bad shape");
     MOMA_REQUIRE(part_m && part_l && part_mmax && part_O && q_f32 && kpos_f32 && loss_rows && dq_unit && pos_is_max,
                  MOMA_ERR_INVALID, "nce_combine: null pointer");
-    nce_combine_kernel<<<(unsigned)B, 128, 0, as_stream(stream)>>>(
+    nce_reduce_kernel<true><<<(unsigned)B, kCombThreads, 0, as_stream(stream)>>>(
         part_m, part_l, part_mmax, part_O, n_parts, q_f32, kpos_f32, (int)B, (int)D, inv_T,
-        loss_rows, dq_unit, pos_is_max, max_logit);
+        loss_rows, dq_unit, pos_is_max, max_logit, nullptr);
     MOMA_CUDA_LAUNCH_CHECK("nce_combine");
     note_launches(1);
     return MOMA_OK;
@@ -422,8 +439,9 @@ extern "C" __attribute__((visibility("default"))) int moma_nce_merge(
     MOMA_REQUIRE(B > 0 && D > 0 && n_parts > 0, MOMA_ERR_INVALID, "nce_merge: bad shape");
     MOMA_REQUIRE(part_m && part_l && part_mmax && part_O && out_m && out_l && out_mmax && out_O,
                  MOMA_ERR_INVALID, "nce_merge: null pointer");
-    nce_merge_kernel<<<(unsigned)B, 128, 0, as_stream(stream)>>>(part_m, part_l, part_mmax, part_O, n_parts,
-                                                                (int)B, (int)D, out_m, out_l, out_mmax, out_O);
+    nce_reduce_kernel<false><<<(unsigned)B, kCombThreads, 0, as_stream(stream)>>>(
+        part_m, part_l, part_mmax, part_O, n_parts, nullptr, nullptr, (int)B, (int)D, 1.f, out_m, out_O, nullptr,
+        out_l, out_mmax);
     MOMA_CUDA_LAUNCH_CHECK("nce_merge");
     note_launches(1);
     return MOMA_OK;

@@ -38,6 +38,24 @@ class BaseMoCo(nn.Module):
     def _update_pointer(self, bsz):
         # mem_moco.py:14-15
         self.index = (self.index + bsz) % self.K
+        if self._index_dev is not None:         # device mirror, advanced on the stream (CUDA graphs)
+            ops.pointer_advance(self._index_dev, bsz, self.K)
+
+    _index_dev = None
+
+    def use_device_pointer(self, device=None, enable=True):
+        """Mirror ``index`` in a device-resident int64 that the enqueue kernel reads and a tiny
+        kernel advances, so a captured CUDA graph of the step stays correct across replays.  The
+        host ``index`` attribute keeps the reference's semantics (``replayed(n)`` re-syncs it)."""
+        if not enable:
+            self._index_dev = None
+            return
+        device = device or next(self.buffers()).device
+        self._index_dev = torch.tensor([self.index], dtype=torch.int64, device=device)
+
+    def replayed(self, n_rows):
+        """Account on the host for one graph replay that enqueued ``n_rows`` rows."""
+        self.index = (self.index + n_rows) % self.K
 
     def _shadow_of(self, queue: torch.Tensor, create: bool = True):
         """bf16 shadow of a queue buffer, rebuilt when the fp32 master was replaced or
@@ -66,7 +84,7 @@ class BaseMoCo(nn.Module):
                 raise RuntimeError(f"enqueue of {k.shape[0]} rows into a queue of K={self.K}: duplicate ids "
                                    "(undefined in the reference, mem_moco.py:24-27)")
             shadow = self._shadow_of(queue, create=ops.get_precision() == "bf16")
-            ops.enqueue(k, queue, shadow, self.K, self.index)
+            ops.enqueue(k, queue, shadow, self.K, self.index, index_dev=self._index_dev)
 
     # ---- logits -----------------------------------------------------------
     def _compute_logit(self, q, k, queue):

@@ -153,6 +153,10 @@ def enqueue(keys: torch.Tensor, queue: torch.Tensor, shadow: Optional[torch.Tens
                                    _p(index_dev), rank, world, int(normalize), eps, _stream()))
 
 
+def pointer_advance(index_dev: torch.Tensor, n: int, K: int) -> None:
+    check(_lib.load().moma_pointer_advance(_p(index_dev), int(n), int(K), _stream()))
+
+
 def enqueue_ids(n: int, index: int, K: int, device) -> torch.Tensor:
     out = torch.empty(n, dtype=torch.int64, device=device)
     check(_lib.load().moma_enqueue_ids(n, int(index), None, K, _p(out), _stream()))

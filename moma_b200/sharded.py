@@ -141,7 +141,7 @@ class ShardedMoCo(BaseMoCo):
             if all_k.shape[0] > self.K:
                 raise RuntimeError("enqueue of more rows than K (duplicate ids)")
             ops.enqueue(all_k, self.memory_shard, shadow if use_bf16 else self._shadow_of(self.memory_shard, create=False),
-                        self.K, self.index, rank=self.rank, world=W)
+                        self.K, self.index, rank=self.rank, world=W, index_dev=self._index_dev)
         self._update_pointer(all_k.size(0))
         return logits, labels
 
