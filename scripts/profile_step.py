@@ -1,0 +1,53 @@
+"""Kernel-level timeline of graph replays of the criterion step via torch.profiler (CUPTI)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from torch.profiler import ProfilerActivity, profile
+from bench import CONFIGS, CriterionStep
+from moma_b200.graphed import GraphedStep
+
+cfg = CONFIGS[sys.argv[1] if len(sys.argv) > 1 else "C2"]
+mode = sys.argv[2] if len(sys.argv) > 2 else "seq"
+dev = torch.device("cuda", 0)
+torch.cuda.set_stream(torch.cuda.Stream(dev))
+cs = CriterionStep(cfg, 0, 1, dev)
+g = GraphedStep(cs.step if mode == "seq" else cs.step_overlapped, contrast=cs.contrast, rows_per_step=cfg["B"])
+for _ in range(5):
+    g.replay()
+torch.cuda.synchronize()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if len(sys.argv) > 3 and sys.argv[3] == "flush" else None
+# event timing as bench.py does it
+for cold in (True, False):
+    ts = []
+    for _ in range(30):
+        if cold and flush is not None:
+            flush.fill_(1)
+        else:
+            torch.cuda._sleep(100000)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); g.replay(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3)
+    ts.sort()
+    print("event-timed replay", "cold" if cold and flush is not None else "warm", f"{ts[len(ts)//2]:.1f} us")
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    for _ in range(3):
+        if flush is not None:
+            flush.fill_(1)
+        g.replay()
+    torch.cuda.synchronize()
+evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+evs.sort(key=lambda e: e.time_range.start)
+# last replay only
+n = len(evs) // 3
+last = evs[-n:]
+t0 = last[0].time_range.start
+busy = 0.0
+prev_end = t0
+print(f"{'start':>8s} {'dur':>7s} {'gap':>6s}  kernel")
+for e in last:
+    st, en = e.time_range.start - t0, e.time_range.end - t0
+    print(f"{st:8.1f} {en - st:7.1f} {e.time_range.start - prev_end:6.1f}  {e.name[:90]}")
+    busy += en - st
+    prev_end = max(prev_end, e.time_range.end)
+print(f"total span {prev_end - t0:.1f} us, sum of kernel durations {busy:.1f} us, kernels {len(last)}")
