@@ -127,8 +127,13 @@ int moma_nce_partial(const void *q, const void *queue, int64_t B, int64_t D, int
                      float *part_mmax, float *part_O, moma_stream_t stream);
 int moma_nce_combine(const float *part_m, const float *part_l, const float *part_mmax,
                      const float *part_O, int n_parts, const float *q_f32, const float *kpos_f32,
-                     int64_t B, int64_t D, float inv_T, float *loss_rows, float *dq_unit,
-                     int32_t *pos_is_max, float *max_logit /* nullable: max_j l_ij */,
+                     int64_t B, int64_t D, float inv_T,
+                     int round_bf16 /* round q / kpos to bf16 inline (bf16 mode) */,
+                     float dq_scale /* folded into dq_unit, e.g. 1/B for the mean */,
+                     float *loss_rows, float *dq_unit, int32_t *pos_is_max,
+                     float *max_logit /* nullable: max_j l_ij */,
+                     float *loss_mean /* nullable pair: mean_i loss_rows[i] ... */,
+                     float *acc_pct /* ... and 100 * mean_i pos_is_max[i] (learning/util.py:25-41) */,
                      moma_stream_t stream);
 /* Fold `n_parts` partials into ONE partial per row (same (m, l, mmax, O) convention); used by
  * the K-sharded queue before the cross-rank exchange. */

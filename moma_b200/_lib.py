@@ -33,7 +33,8 @@ SIGNATURES = {
     "moma_cast_bf16": (c_int, [_vp, _vp, _i64, _vp]),
     "moma_nce_num_splits": (c_int, [_i64, _i64, _i64, c_int]),
     "moma_nce_partial": (c_int, [_vp, _vp, _i64, _i64, _i64, c_float, c_int, c_int, _vp, _vp, _vp, _vp, _vp]),
-    "moma_nce_combine": (c_int, [_vp, _vp, _vp, _vp, c_int, _vp, _vp, _i64, _i64, c_float, _vp, _vp, _vp, _vp, _vp]),
+    "moma_nce_combine": (c_int, [_vp, _vp, _vp, _vp, c_int, _vp, _vp, _i64, _i64, c_float, c_int, c_float,
+                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "moma_nce_merge": (c_int, [_vp, _vp, _vp, _vp, c_int, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "moma_nce_logits": (c_int, [_vp, _vp, _vp, _i64, _i64, _i64, c_float, c_int, _vp, _vp]),
     "moma_nce_logits_qk": (c_int, [_vp, _vp, _i64, _i64, c_float, _vp, _vp]),

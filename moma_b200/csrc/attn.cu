@@ -17,16 +17,16 @@ namespace moma {
 // The GEMMs of this path are tiny (M, N, K in the hundreds) and latency-bound, so the kernel is
 // built for few dependent phases and many CTAs: 32x32 output tile per 128-thread CTA, the whole
 // K strip (up to 128) staged in shared memory in ONE load phase, 128-bit shared-memory reads.
-constexpr int kGM = 32, kGN = 32, kGK = 128, kGLd = kGK + 4, kGThreads = 128;
+constexpr int kGN = 32, kGK = 128, kGLd = kGK + 4, kGThreads = 128;
 
-template <bool KCONTIG>
+template <bool KCONTIG, int ROWS>
 __device__ __forceinline__ void load_strip(float* dst, const float* __restrict__ src, int64_t rs, int64_t cs,
                                            int r0, int R, int k0, int K, bool vec_ok) {
     const int tid = threadIdx.x;
     if (KCONTIG) {
         // consecutive lanes walk along k (contiguous): float4 when aligned
 #pragma unroll
-        for (int i = 0; i < (32 * kGK / 4) / kGThreads; ++i) {
+        for (int i = 0; i < (ROWS * kGK / 4) / kGThreads; ++i) {
             const int idx = tid + i * kGThreads;
             const int r = idx >> 5, v = idx & 31;
             const int k = k0 + 4 * v;
@@ -46,46 +46,48 @@ __device__ __forceinline__ void load_strip(float* dst, const float* __restrict__
     } else {
         // consecutive lanes walk along the row index (contiguous in memory), k strided by cs
 #pragma unroll 8
-        for (int i = 0; i < (32 * kGK) / kGThreads; ++i) {
+        for (int i = 0; i < (ROWS * kGK) / kGThreads; ++i) {
             const int idx = tid + i * kGThreads;
-            const int r = idx & 31, k = idx >> 5;
+            const int r = idx % ROWS, k = idx / ROWS;
             dst[r * kGLd + k] = (r0 + r < R && k0 + k < K) ? src[(int64_t)(k0 + k) * cs + (r0 + r)] : 0.f;
         }
     }
 }
 
-template <bool A_KCONTIG, bool B_KCONTIG>
+// TM = 32 or 16 output rows per CTA (16 when the 32-row grid would leave most SMs idle)
+template <bool A_KCONTIG, bool B_KCONTIG, int TM>
 __global__ void __launch_bounds__(kGThreads)
 sgemm_kernel(const float* __restrict__ A, int64_t a_rs, int64_t a_cs, const float* __restrict__ Bm,
              int64_t b_rs, int64_t b_cs, const float* __restrict__ bias, float* __restrict__ Cm,
              int64_t ldc, int M, int N, int K, int a_vec, int b_vec) {
-    __shared__ __align__(16) float As[kGM * kGLd];
+    __shared__ __align__(16) float As[TM * kGLd];
     __shared__ __align__(16) float Bs[kGN * kGLd];
+    constexpr int RT = TM / 16;                                  // rows per thread
     const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
-    const int m0 = blockIdx.y * kGM, n0 = blockIdx.x * kGN;
-    float acc[2][4] = {};
+    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * kGN;
+    float acc[RT][4] = {};
     for (int k0 = 0; k0 < K; k0 += kGK) {
         if (k0 > 0) __syncthreads();
-        load_strip<A_KCONTIG>(As, A, a_rs, a_cs, m0, M, k0, K, a_vec != 0);
-        load_strip<B_KCONTIG>(Bs, Bm, b_rs, b_cs, n0, N, k0, K, b_vec != 0);
+        load_strip<A_KCONTIG, TM>(As, A, a_rs, a_cs, m0, M, k0, K, a_vec != 0);
+        load_strip<B_KCONTIG, kGN>(Bs, Bm, b_rs, b_cs, n0, N, k0, K, b_vec != 0);
         __syncthreads();
         const int kend = min(kGK, K - k0);
 #pragma unroll 4
         for (int k = 0; k < kend; k += 4) {
-            float4 a[2], b[4];
+            float4 a[RT], b[4];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) a[i] = *reinterpret_cast<const float4*>(As + (ty + 16 * i) * kGLd + k);
+            for (int i = 0; i < RT; ++i) a[i] = *reinterpret_cast<const float4*>(As + (ty + 16 * i) * kGLd + k);
 #pragma unroll
             for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4*>(Bs + (tx + 8 * j) * kGLd + k);
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
+            for (int i = 0; i < RT; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     acc[i][j] += a[i].x * b[j].x + a[i].y * b[j].y + a[i].z * b[j].z + a[i].w * b[j].w;
         }
     }
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < RT; ++i) {
         const int r = m0 + ty + 16 * i;
         if (r >= M) continue;
 #pragma unroll
@@ -96,16 +98,24 @@ sgemm_kernel(const float* __restrict__ A, int64_t a_rs, int64_t a_cs, const floa
     }
 }
 
+template <int TM>
+static void sgemm_tm(const float* A, int64_t a_rs, int64_t a_cs, const float* Bm, int64_t b_rs,
+                     int64_t b_cs, const float* bias, float* Cm, int64_t ldc, int M, int N, int K, cudaStream_t st) {
+    const dim3 grid((N + kGN - 1) / kGN, (M + TM - 1) / TM);
+    const bool ak = (a_cs == 1), bk = (b_cs == 1);
+    const int av = ak && (a_rs % 4 == 0) && aligned16(A), bv = bk && (b_rs % 4 == 0) && aligned16(Bm);
+    if (ak && bk) sgemm_kernel<true, true, TM><<<grid, kGThreads, 0, st>>>(A, a_rs, a_cs, Bm, b_rs, b_cs, bias, Cm, ldc, M, N, K, av, bv);
+    else if (ak && !bk) sgemm_kernel<true, false, TM><<<grid, kGThreads, 0, st>>>(A, a_rs, a_cs, Bm, b_rs, b_cs, bias, Cm, ldc, M, N, K, av, bv);
+    else if (!ak && bk) sgemm_kernel<false, true, TM><<<grid, kGThreads, 0, st>>>(A, a_rs, a_cs, Bm, b_rs, b_cs, bias, Cm, ldc, M, N, K, av, bv);
+    else sgemm_kernel<false, false, TM><<<grid, kGThreads, 0, st>>>(A, a_rs, a_cs, Bm, b_rs, b_cs, bias, Cm, ldc, M, N, K, av, bv);
+}
+
 static void sgemm(const float* A, int64_t a_rs, int64_t a_cs, const float* Bm, int64_t b_rs,
                   int64_t b_cs, const float* bias, float* Cm, int64_t ldc, int M, int N, int K,
                   cudaStream_t st) {
-    const dim3 grid((N + kGN - 1) / kGN, (M + kGM - 1) / kGM);
-    const bool ak = (a_cs == 1), bk = (b_cs == 1);
-    const int av = ak && (a_rs % 4 == 0) && aligned16(A), bv = bk && (b_rs % 4 == 0) && aligned16(Bm);
-    if (ak && bk) sgemm_kernel<true, true><<<grid, kGThreads, 0, st>>>(A, a_rs, a_cs, Bm, b_rs, b_cs, bias, Cm, ldc, M, N, K, av, bv);
-    else if (ak && !bk) sgemm_kernel<true, false><<<grid, kGThreads, 0, st>>>(A, a_rs, a_cs, Bm, b_rs, b_cs, bias, Cm, ldc, M, N, K, av, bv);
-    else if (!ak && bk) sgemm_kernel<false, true><<<grid, kGThreads, 0, st>>>(A, a_rs, a_cs, Bm, b_rs, b_cs, bias, Cm, ldc, M, N, K, av, bv);
-    else sgemm_kernel<false, false><<<grid, kGThreads, 0, st>>>(A, a_rs, a_cs, Bm, b_rs, b_cs, bias, Cm, ldc, M, N, K, av, bv);
+    const int ctas32 = ((N + kGN - 1) / kGN) * ((M + 31) / 32);
+    if (ctas32 >= sm_count() * 3 / 4) sgemm_tm<32>(A, a_rs, a_cs, Bm, b_rs, b_cs, bias, Cm, ldc, M, N, K, st);
+    else sgemm_tm<16>(A, a_rs, a_cs, Bm, b_rs, b_cs, bias, Cm, ldc, M, N, K, st);
 }
 
 // column sums: out[c] = sum_r X[r, c]   (bias gradients)
@@ -128,16 +138,18 @@ colsum_kernel(const float* __restrict__ X, int rows, int cols, float* __restrict
 }
 
 // ------------------------------------------------------------------ fused attention core
-// Tiles: 32 "row" tokens per CTA (8 per warp, 4 warps) against KT "column" tokens per step.  KT is as
-// wide as shared memory allows (256 for head_dim <= 32) so that at the path's sizes (N = 256..1024)
-// a CTA goes through 1-4 load phases instead of N/64: these kernels are latency-bound.
-constexpr int kAR = 32;    // rows per CTA
+// Tiles: 4*RW "row" tokens per CTA (RW per warp, 4 warps) against KT "column" tokens per step.  KT is
+// as wide as shared memory allows (256 for head_dim <= 32) so that at the path's sizes (N = 256..1024)
+// a CTA goes through 1-4 load phases instead of N/64, and RW (8, 4 or 2) is picked at launch so the
+// grid has about one CTA per SM: these kernels are latency-bound, not FLOP-bound.
 constexpr int kAThreads = 128;
 
-template <int HD> struct AttnCfg {
+template <int HD, int RW> struct AttnCfg {
+    static constexpr int AR = 4 * RW;                       // rows per CTA
     static constexpr int LD = HD + 4;                       // padded smem row (floats)
     static constexpr int CPL = HD >= 32 ? HD / 32 : 1;      // output columns per lane
-    static constexpr int RPL = HD >= 32 ? 8 : HD / 4;       // output rows per lane (32/HD row groups)
+    static constexpr int RPL = HD >= 32 ? RW : RW * HD / 32;   // output rows per lane (32/HD row groups)
+    static_assert(RW * HD >= 32, "too few rows per warp for this head_dim");
     static constexpr int KT_FWD = HD <= 32 ? 256 : (HD == 64 ? 128 : 64);   // column tile, forward
     static constexpr int KT_BWD = HD <= 32 ? 128 : 64;                      // column tile, backward (2 score tiles live)
     __device__ static int roff(int lane) { return HD >= 32 ? 0 : (lane / HD) * RPL; }
@@ -157,13 +169,13 @@ __device__ __forceinline__ void load_rows(float* dst, const float* __restrict__ 
     }
 }
 
-// s[r][cc] = sum_d a[warp*8 + r][d] * b[lane + 32*cc][d],  cc < KT/32
-template <int HD, int KT>
+// s[r][cc] = sum_d a[warp*RW + r][d] * b[lane + 32*cc][d],  cc < KT/32
+template <int HD, int KT, int RW>
 __device__ __forceinline__ void dot_tile(const float* a_s, const float* b_s, int warp, int lane,
-                                         float (&s)[8][KT / 32]) {
+                                         float (&s)[RW][KT / 32]) {
     constexpr int LD = HD + 4, CC = KT / 32;
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
+    for (int r = 0; r < RW; ++r)
 #pragma unroll
         for (int cc = 0; cc < CC; ++cc) s[r][cc] = 0.f;
 #pragma unroll 2
@@ -172,8 +184,8 @@ __device__ __forceinline__ void dot_tile(const float* a_s, const float* b_s, int
 #pragma unroll
         for (int cc = 0; cc < CC; ++cc) b[cc] = *reinterpret_cast<const float4*>(b_s + (lane + 32 * cc) * LD + 4 * v);
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const float4 a = *reinterpret_cast<const float4*>(a_s + (warp * 8 + r) * LD + 4 * v);
+        for (int r = 0; r < RW; ++r) {
+            const float4 a = *reinterpret_cast<const float4*>(a_s + (warp * RW + r) * LD + 4 * v);
 #pragma unroll
             for (int cc = 0; cc < CC; ++cc)
                 s[r][cc] += a.x * b[cc].x + a.y * b[cc].y + a.z * b[cc].z + a.w * b[cc].w;
@@ -182,12 +194,12 @@ __device__ __forceinline__ void dot_tile(const float* a_s, const float* b_s, int
 }
 
 // acc[r][c] += sum_j p[row(r)][j] * v[j][col(c)],  j over the KT-column tile
-template <int HD, int KT>
+template <int HD, int KT, int RW>
 __device__ __forceinline__ void acc_tile(const float* p_s, const float* v_s, int warp, int lane,
-                                         float (&acc)[AttnCfg<HD>::RPL][AttnCfg<HD>::CPL]) {
-    using Cfg = AttnCfg<HD>;
+                                         float (&acc)[AttnCfg<HD, RW>::RPL][AttnCfg<HD, RW>::CPL]) {
+    using Cfg = AttnCfg<HD, RW>;
     constexpr int LD = Cfg::LD, LDP = KT + 4;
-    const int rbase = warp * 8 + Cfg::roff(lane);
+    const int rbase = warp * RW + Cfg::roff(lane);
     const int cbase = Cfg::cbase(lane);
 #pragma unroll 2
     for (int j = 0; j < KT; j += 4) {
@@ -207,11 +219,12 @@ __device__ __forceinline__ void acc_tile(const float* p_s, const float* v_s, int
 }
 
 // ---- forward: grid (ceil(N/32), H)
-template <int HD>
+template <int HD, int RW>
 __global__ void __launch_bounds__(kAThreads)
 attn_fwd_kernel(const float* __restrict__ qkv, int N, int C, float scale, float* __restrict__ o,
                 float* __restrict__ lse) {
-    using Cfg = AttnCfg<HD>;
+    using Cfg = AttnCfg<HD, RW>;
+    constexpr int kAR = Cfg::AR;
     constexpr int KT = Cfg::KT_FWD, CC = KT / 32, LDP = KT + 4;
     extern __shared__ __align__(16) float sm[];
     float* q_s = sm;                         // [32][LD]
@@ -226,9 +239,9 @@ attn_fwd_kernel(const float* __restrict__ qkv, int N, int C, float scale, float*
     const float* vg = qkv + 2 * C + h * HD;
 
     load_rows<HD>(q_s, qg, ldg, i0, kAR, N);
-    float m_run[8], l_run[8];
+    float m_run[RW], l_run[RW];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) { m_run[r] = -CUDART_INF_F; l_run[r] = 0.f; }
+    for (int r = 0; r < RW; ++r) { m_run[r] = -CUDART_INF_F; l_run[r] = 0.f; }
     float acc[Cfg::RPL][Cfg::CPL] = {};
     const int roff = Cfg::roff(lane);
 
@@ -237,11 +250,11 @@ attn_fwd_kernel(const float* __restrict__ qkv, int N, int C, float scale, float*
         load_rows<HD>(k_s, kg, ldg, j0, KT, N);
         load_rows<HD>(v_s, vg, ldg, j0, KT, N);
         __syncthreads();
-        float s[8][CC];
-        dot_tile<HD, KT>(q_s, k_s, warp, lane, s);
-        float corr[8];
+        float s[RW][CC];
+        dot_tile<HD, KT, RW>(q_s, k_s, warp, lane, s);
+        float corr[RW];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
+        for (int r = 0; r < RW; ++r) {
             float mx = -CUDART_INF_F;
 #pragma unroll
             for (int cc = 0; cc < CC; ++cc) {
@@ -255,7 +268,7 @@ attn_fwd_kernel(const float* __restrict__ qkv, int N, int C, float scale, float*
 #pragma unroll
             for (int cc = 0; cc < CC; ++cc) {
                 const float p = (s[r][cc] == -CUDART_INF_F) ? 0.f : expf(s[r][cc] - m_new);
-                p_s[(warp * 8 + r) * LDP + lane + 32 * cc] = p;
+                p_s[(warp * RW + r) * LDP + lane + 32 * cc] = p;
                 sum += p;
             }
             l_run[r] = l_run[r] * corr[r] + warp_sum(sum);
@@ -265,31 +278,31 @@ attn_fwd_kernel(const float* __restrict__ qkv, int N, int C, float scale, float*
         for (int r = 0; r < Cfg::RPL; ++r) {
             float cr = corr[0];                 // corr is warp-uniform per row; pick this lane's rows
 #pragma unroll
-            for (int rr = 0; rr < 8; ++rr) cr = (rr == r + roff) ? corr[rr] : cr;
+            for (int rr = 0; rr < RW; ++rr) cr = (rr == r + roff) ? corr[rr] : cr;
 #pragma unroll
             for (int c = 0; c < Cfg::CPL; ++c) acc[r][c] *= cr;
         }
         __syncwarp();
-        acc_tile<HD, KT>(p_s, v_s, warp, lane, acc);
+        acc_tile<HD, KT, RW>(p_s, v_s, warp, lane, acc);
     }
     const int cbase = Cfg::cbase(lane);
 #pragma unroll
     for (int r = 0; r < Cfg::RPL; ++r) {
         float lr = l_run[0];
 #pragma unroll
-        for (int rr = 0; rr < 8; ++rr) lr = (rr == r + roff) ? l_run[rr] : lr;
-        const int row = i0 + warp * 8 + roff + r;
+        for (int rr = 0; rr < RW; ++rr) lr = (rr == r + roff) ? l_run[rr] : lr;
+        const int row = i0 + warp * RW + roff + r;
         if (row < N) {
 #pragma unroll
             for (int c = 0; c < Cfg::CPL; ++c)
                 o[(int64_t)row * C + h * HD + cbase + 32 * c] = acc[r][c] / lr;
         }
     }
-    if (lane < 8) {
+    if (lane < RW) {
         float mr = m_run[0], lr = l_run[0];
 #pragma unroll
-        for (int rr = 0; rr < 8; ++rr) { mr = (rr == lane) ? m_run[rr] : mr; lr = (rr == lane) ? l_run[rr] : lr; }
-        const int row = i0 + warp * 8 + lane;
+        for (int rr = 0; rr < RW; ++rr) { mr = (rr == lane) ? m_run[rr] : mr; lr = (rr == lane) ? l_run[rr] : lr; }
+        const int row = i0 + warp * RW + lane;
         if (row < N) lse[(int64_t)h * N + row] = mr + logf(lr);
     }
 }
@@ -327,12 +340,13 @@ attn_delta_kernel(const float* __restrict__ dO, const float* __restrict__ o, int
 }
 
 // dQ: grid (ceil(N/32) query blocks, H)
-template <int HD>
+template <int HD, int RW>
 __global__ void __launch_bounds__(kAThreads)
 attn_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
                    const float* __restrict__ lse, const float* __restrict__ delta, int N, int C,
                    float scale, float* __restrict__ dqkv) {
-    using Cfg = AttnCfg<HD>;
+    using Cfg = AttnCfg<HD, RW>;
+    constexpr int kAR = Cfg::AR;
     constexpr int KT = Cfg::KT_BWD, CC = KT / 32, LDP = KT + 4;
     extern __shared__ __align__(16) float sm[];
     float* q_s = sm;                          // [32][LD]
@@ -345,10 +359,10 @@ attn_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
     const int64_t ldg = 3 * (int64_t)C;
     load_rows<HD>(q_s, qkv + h * HD, ldg, i0, kAR, N);
     load_rows<HD>(do_s, dO + h * HD, C, i0, kAR, N);
-    float lse_r[8], del_r[8];
+    float lse_r[RW], del_r[RW];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        const int row = i0 + warp * 8 + r;
+    for (int r = 0; r < RW; ++r) {
+        const int row = i0 + warp * RW + r;
         lse_r[r] = row < N ? lse[(int64_t)h * N + row] : 0.f;
         del_r[r] = row < N ? delta[(int64_t)h * N + row] : 0.f;
     }
@@ -358,26 +372,26 @@ attn_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
         load_rows<HD>(k_s, qkv + C + h * HD, ldg, j0, KT, N);
         load_rows<HD>(v_s, qkv + 2 * C + h * HD, ldg, j0, KT, N);
         __syncthreads();
-        float s[8][CC], dp[8][CC];
-        dot_tile<HD, KT>(q_s, k_s, warp, lane, s);
-        dot_tile<HD, KT>(do_s, v_s, warp, lane, dp);
+        float s[RW][CC], dp[RW][CC];
+        dot_tile<HD, KT, RW>(q_s, k_s, warp, lane, s);
+        dot_tile<HD, KT, RW>(do_s, v_s, warp, lane, dp);
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
+        for (int r = 0; r < RW; ++r) {
 #pragma unroll
             for (int cc = 0; cc < CC; ++cc) {
                 const bool ok = (j0 + lane + 32 * cc < N);
                 const float p = ok ? expf(s[r][cc] * scale - lse_r[r]) : 0.f;
-                p_s[(warp * 8 + r) * LDP + lane + 32 * cc] = p * (dp[r][cc] - del_r[r]);
+                p_s[(warp * RW + r) * LDP + lane + 32 * cc] = p * (dp[r][cc] - del_r[r]);
             }
         }
         __syncwarp();
-        acc_tile<HD, KT>(p_s, k_s, warp, lane, acc);
+        acc_tile<HD, KT, RW>(p_s, k_s, warp, lane, acc);
     }
     const int roff = Cfg::roff(lane);
     const int cbase = Cfg::cbase(lane);
 #pragma unroll
     for (int r = 0; r < Cfg::RPL; ++r) {
-        const int row = i0 + warp * 8 + roff + r;
+        const int row = i0 + warp * RW + roff + r;
         if (row < N)
 #pragma unroll
             for (int c = 0; c < Cfg::CPL; ++c)
@@ -386,12 +400,13 @@ attn_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
 }
 
 // dK, dV: grid (ceil(N/32) key blocks, H); rows = keys, columns = queries
-template <int HD>
+template <int HD, int RW>
 __global__ void __launch_bounds__(kAThreads)
 attn_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
                     const float* __restrict__ lse, const float* __restrict__ delta, int N, int C,
                     float scale, float* __restrict__ dqkv) {
-    using Cfg = AttnCfg<HD>;
+    using Cfg = AttnCfg<HD, RW>;
+    constexpr int kAR = Cfg::AR;
     constexpr int KT = Cfg::KT_BWD, CC = KT / 32, LDP = KT + 4;
     extern __shared__ __align__(16) float sm[];
     float* k_s = sm;                           // [32][LD]  own keys
@@ -412,9 +427,9 @@ attn_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
         load_rows<HD>(q_s, qkv + h * HD, ldg, i0, KT, N);
         load_rows<HD>(do_s, dO + h * HD, C, i0, KT, N);
         __syncthreads();
-        float st[8][CC], dpt[8][CC];
-        dot_tile<HD, KT>(k_s, q_s, warp, lane, st);      // st[r][cc] = k_j . q_i
-        dot_tile<HD, KT>(v_s, do_s, warp, lane, dpt);    // dpt      = v_j . do_i
+        float st[RW][CC], dpt[RW][CC];
+        dot_tile<HD, KT, RW>(k_s, q_s, warp, lane, st);      // st[r][cc] = k_j . q_i
+        dot_tile<HD, KT, RW>(v_s, do_s, warp, lane, dpt);    // dpt      = v_j . do_i
         float lse_c[CC], del_c[CC];
 #pragma unroll
         for (int cc = 0; cc < CC; ++cc) {
@@ -423,25 +438,25 @@ attn_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
             del_c[cc] = i < N ? delta[(int64_t)h * N + i] : 0.f;
         }
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const bool rok = (j0 + warp * 8 + r < N);
+        for (int r = 0; r < RW; ++r) {
+            const bool rok = (j0 + warp * RW + r < N);
 #pragma unroll
             for (int cc = 0; cc < CC; ++cc) {
                 const bool ok = rok && (i0 + lane + 32 * cc < N);
                 const float p = ok ? expf(st[r][cc] * scale - lse_c[cc]) : 0.f;
-                p_s[(warp * 8 + r) * LDP + lane + 32 * cc] = p;
-                ds_s[(warp * 8 + r) * LDP + lane + 32 * cc] = p * (dpt[r][cc] - del_c[cc]);
+                p_s[(warp * RW + r) * LDP + lane + 32 * cc] = p;
+                ds_s[(warp * RW + r) * LDP + lane + 32 * cc] = p * (dpt[r][cc] - del_c[cc]);
             }
         }
         __syncwarp();
-        acc_tile<HD, KT>(p_s, do_s, warp, lane, acc_v);
-        acc_tile<HD, KT>(ds_s, q_s, warp, lane, acc_k);
+        acc_tile<HD, KT, RW>(p_s, do_s, warp, lane, acc_v);
+        acc_tile<HD, KT, RW>(ds_s, q_s, warp, lane, acc_k);
     }
     const int roff = Cfg::roff(lane);
     const int cbase = Cfg::cbase(lane);
 #pragma unroll
     for (int r = 0; r < Cfg::RPL; ++r) {
-        const int row = j0 + warp * 8 + roff + r;
+        const int row = j0 + warp * RW + roff + r;
         if (row < N)
 #pragma unroll
             for (int c = 0; c < Cfg::CPL; ++c) {
@@ -451,37 +466,67 @@ attn_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
     }
 }
 
-template <int HD> static size_t fwd_smem() {
-    constexpr int KT = AttnCfg<HD>::KT_FWD;
-    return (size_t)((kAR + 2 * KT) * (HD + 4) + kAR * (KT + 4)) * sizeof(float);
+template <int HD, int RW> static size_t fwd_smem() {
+    constexpr int KT = AttnCfg<HD, RW>::KT_FWD, AR = 4 * RW;
+    return (size_t)((AR + 2 * KT) * (HD + 4) + AR * (KT + 4)) * sizeof(float);
 }
-template <int HD> static size_t dq_smem() {
-    constexpr int KT = AttnCfg<HD>::KT_BWD;
-    return (size_t)((2 * kAR + 2 * KT) * (HD + 4) + kAR * (KT + 4)) * sizeof(float);
+template <int HD, int RW> static size_t dq_smem() {
+    constexpr int KT = AttnCfg<HD, RW>::KT_BWD, AR = 4 * RW;
+    return (size_t)((2 * AR + 2 * KT) * (HD + 4) + AR * (KT + 4)) * sizeof(float);
 }
-template <int HD> static size_t dkv_smem() {
-    constexpr int KT = AttnCfg<HD>::KT_BWD;
-    return (size_t)((2 * kAR + 2 * KT) * (HD + 4) + 2 * kAR * (KT + 4)) * sizeof(float);
+template <int HD, int RW> static size_t dkv_smem() {
+    constexpr int KT = AttnCfg<HD, RW>::KT_BWD, AR = 4 * RW;
+    return (size_t)((2 * AR + 2 * KT) * (HD + 4) + 2 * AR * (KT + 4)) * sizeof(float);
 }
 
+template <int HD, int RW>
+static void launch_fwd_rw(const float* qkv, int N, int C, int H, float scale, float* o, float* lse, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(attn_fwd_kernel<HD, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<HD, RW>()); attr = true; }
+    constexpr int AR = 4 * RW;
+    attn_fwd_kernel<HD, RW><<<dim3((N + AR - 1) / AR, H), kAThreads, fwd_smem<HD, RW>(), st>>>(qkv, N, C, scale, o, lse);
+}
+template <int HD, int RW>
+static void launch_bwd_rw(const float* qkv, const float* dO, const float* lse, const float* delta, int N, int C, int H,
+                          float scale, float* dqkv, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(attn_bwd_dq_kernel<HD, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dq_smem<HD, RW>());
+        cudaFuncSetAttribute(attn_bwd_dkv_kernel<HD, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dkv_smem<HD, RW>());
+        attr = true;
+    }
+    constexpr int AR = 4 * RW;
+    const dim3 grid((N + AR - 1) / AR, H);
+    attn_bwd_dq_kernel<HD, RW><<<grid, kAThreads, dq_smem<HD, RW>(), st>>>(qkv, dO, lse, delta, N, C, scale, dqkv);
+    attn_bwd_dkv_kernel<HD, RW><<<grid, kAThreads, dkv_smem<HD, RW>(), st>>>(qkv, dO, lse, delta, N, C, scale, dqkv);
+}
+
+// rows per warp: the largest of {8, 4, 2} (but RW * HD >= 32) that still gives about one CTA per SM
+template <int HD> static int pick_rw(int N, int H) {
+    constexpr int rw_min = HD >= 16 ? 2 : 4;
+    const int target = sm_count() * 3 / 4;
+    for (int rw = 8; rw > rw_min; rw >>= 1)
+        if (((N + 4 * rw - 1) / (4 * rw)) * H >= target) return rw;
+    return rw_min;
+}
 template <int HD>
 static void launch_fwd(const float* qkv, int N, int C, int H, float scale, float* o, float* lse, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(attn_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<HD>()); attr = true; }
-    attn_fwd_kernel<HD><<<dim3((N + kAR - 1) / kAR, H), kAThreads, fwd_smem<HD>(), st>>>(qkv, N, C, scale, o, lse);
+    switch (pick_rw<HD>(N, H)) {
+        case 8: launch_fwd_rw<HD, 8>(qkv, N, C, H, scale, o, lse, st); break;
+        case 4: launch_fwd_rw<HD, 4>(qkv, N, C, H, scale, o, lse, st); break;
+        default: if constexpr (HD >= 16) launch_fwd_rw<HD, 2>(qkv, N, C, H, scale, o, lse, st);
+                 else launch_fwd_rw<HD, 4>(qkv, N, C, H, scale, o, lse, st);
+    }
 }
 template <int HD>
 static void launch_bwd(const float* qkv, const float* dO, const float* lse, const float* delta, int N, int C, int H,
                        float scale, float* dqkv, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(attn_bwd_dq_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dq_smem<HD>());
-        cudaFuncSetAttribute(attn_bwd_dkv_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dkv_smem<HD>());
-        attr = true;
+    switch (pick_rw<HD>(N, H)) {
+        case 8: launch_bwd_rw<HD, 8>(qkv, dO, lse, delta, N, C, H, scale, dqkv, st); break;
+        case 4: launch_bwd_rw<HD, 4>(qkv, dO, lse, delta, N, C, H, scale, dqkv, st); break;
+        default: if constexpr (HD >= 16) launch_bwd_rw<HD, 2>(qkv, dO, lse, delta, N, C, H, scale, dqkv, st);
+                 else launch_bwd_rw<HD, 4>(qkv, dO, lse, delta, N, C, H, scale, dqkv, st);
     }
-    const dim3 grid((N + kAR - 1) / kAR, H);
-    attn_bwd_dq_kernel<HD><<<grid, kAThreads, dq_smem<HD>(), st>>>(qkv, dO, lse, delta, N, C, scale, dqkv);
-    attn_bwd_dkv_kernel<HD><<<grid, kAThreads, dkv_smem<HD>(), st>>>(qkv, dO, lse, delta, N, C, scale, dqkv);
 }
 
 static int check_attn(const char* who, int64_t N, int64_t C, int H) {

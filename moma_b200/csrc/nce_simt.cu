@@ -169,11 +169,13 @@ nce_partial_f32_kernel(const float* __restrict__ q, const float* __restrict__ qu
 }
 
 // ------------------------------------------------------------------ combine / merge
-// One CTA of 128 threads per query row.  Reductions over the partials are spread over the
-// threads (max / weights / l through shuffles + shared memory); the O accumulation keeps one
-// column per thread with the loop over parts unrolled so the loads are in flight together.
+// One CTA of 128 threads (4 warps) per query row.  Scalar reductions over the partials (max, weights,
+// l) are spread over the threads; the O accumulation splits the PARTS over the 4 warps, each lane owning
+// a float4 of columns, with 8 independent 128-bit loads in flight per lane (the kernel is latency-bound:
+// n_parts * D * 4 bytes per row come from L2), then one cross-warp reduction through shared memory.
 constexpr int kCombThreads = 128;
 constexpr int kCombChunk = 512;       // parts staged per pass
+constexpr int kCombMaxD = 512;        // columns per pass (4 float4 per lane)
 
 __device__ __forceinline__ float block_max(float v, float* red) {
     v = warp_max(v);
@@ -191,6 +193,7 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     __syncthreads();
     return v;
 }
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 // kFinal: add the positive column and emit loss / dq / flags; otherwise emit one merged partial.
 template <bool kFinal>
@@ -198,19 +201,25 @@ __global__ void __launch_bounds__(kCombThreads)
 nce_reduce_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l,
                   const float* __restrict__ part_mmax, const float* __restrict__ part_O, int n_parts,
                   const float* __restrict__ q, const float* __restrict__ kpos, int B, int D, float inv_T,
-                  float* __restrict__ out_a /* loss_rows | out_m */, float* __restrict__ out_O /* dq_unit | out_O */,
+                  int round_bf16, float dq_scale,
+                  float* __restrict__ out_a /* loss_rows | out_m */, float* __restrict__ out_O /* dq | out_O */,
                   int32_t* __restrict__ pos_is_max, float* __restrict__ out_b /* max_logit | out_l */,
                   float* __restrict__ out_c /* - | out_mmax */) {
     __shared__ float red[4];
     __shared__ float s_w[kCombChunk];
-    const int row = blockIdx.x, tid = threadIdx.x;
+    __shared__ __align__(16) float s_o[4][kCombMaxD];
+    const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* kr = kFinal ? kpos + (int64_t)row * D : nullptr;
 
     float pos = 0.f;
     if (kFinal) {
         const float* qr = q + (int64_t)row * D;
         float dot = 0.f;
-        for (int d = tid; d < D; d += kCombThreads) dot += qr[d] * kr[d];
+        for (int d = tid; d < D; d += kCombThreads) {
+            const float qv = round_bf16 ? bf16_round(qr[d]) : qr[d];
+            const float kv = round_bf16 ? bf16_round(kr[d]) : kr[d];
+            dot += qv * kv;
+        }
         pos = block_sum(dot, red) * inv_T;
     }
     float mref = -CUDART_INF_F, mtrue = -CUDART_INF_F;
@@ -223,15 +232,12 @@ nce_reduce_kernel(const float* __restrict__ part_m, const float* __restrict__ pa
     const float mstar = kFinal ? fmaxf(mref, pos) : mref;
     const float wpos = kFinal ? expf(pos - mstar) : 0.f;
 
-    float l_part = 0.f;
-    // columns handled by this thread: tid + 128*c, c < 4 per pass (D <= 512 in one pass)
-    for (int d0 = 0; d0 < D; d0 += 4 * kCombThreads) {
-        float o[4];
+    float l_part = 0.f, l_tot = 0.f;
+    const int64_t sstride = (int64_t)B * D;
+    for (int d0 = 0; d0 < D; d0 += kCombMaxD) {
+        float4 o[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int d = d0 + tid + kCombThreads * c;
-            o[c] = (kFinal && d < D) ? wpos * kr[d] : 0.f;
-        }
+        for (int c = 0; c < 4; ++c) o[c] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int s0 = 0; s0 < n_parts; s0 += kCombChunk) {
             const int cnt = min(kCombChunk, n_parts - s0);
             __syncthreads();
@@ -243,51 +249,80 @@ nce_reduce_kernel(const float* __restrict__ part_m, const float* __restrict__ pa
                 if (d0 == 0) l_part += w * part_l[base];
             }
             __syncthreads();
-            const float* Op = part_O + ((int64_t)s0 * B + row) * D;
-            const int64_t sstride = (int64_t)B * D;
+            const float* Op = part_O + ((int64_t)s0 * B + row) * D + d0;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const int d = d0 + tid + kCombThreads * c;
-                if (d < D) {
-                    float acc = o[c];
-                    int s = 0;
-                    for (; s + 8 <= cnt; s += 8) {
-                        float v[8];
+                const int d = 4 * lane + 128 * c;              // column of this lane's float4
+                if (d0 + d < D) {
+                    float4 acc = o[c];
+                    int s = warp;
+                    for (; s + 28 < cnt; s += 32) {            // 8 parts of this warp per round
+                        float4 v[8];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) v[u] = __ldg(Op + (int64_t)(s + u) * sstride + d);
+                        for (int u = 0; u < 8; ++u)
+                            v[u] = __ldg(reinterpret_cast<const float4*>(Op + (int64_t)(s + 4 * u) * sstride + d));
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) acc = fmaf(s_w[s + u], v[u], acc);
+                        for (int u = 0; u < 8; ++u) {
+                            const float w = s_w[s + 4 * u];
+                            acc.x = fmaf(w, v[u].x, acc.x); acc.y = fmaf(w, v[u].y, acc.y);
+                            acc.z = fmaf(w, v[u].z, acc.z); acc.w = fmaf(w, v[u].w, acc.w);
+                        }
                     }
-                    for (; s < cnt; ++s) acc = fmaf(s_w[s], __ldg(Op + (int64_t)s * sstride + d), acc);
+                    for (; s < cnt; s += 4) {
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(Op + (int64_t)s * sstride + d));
+                        const float w = s_w[s];
+                        acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+                        acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+                    }
                     o[c] = acc;
                 }
             }
         }
-        float l = 0.f;
-        if (d0 == 0) {
-            l = block_sum(l_part, red) + wpos;
-            if (tid == 0) red[0] = l;
-            __syncthreads();
-            l_part = l;                  // every thread now holds the total
-        }
-        l = l_part;
+        if (d0 == 0) l_tot = block_sum(l_part, red) + wpos;
+        // cross-warp reduction of the O partial sums
+        __syncthreads();
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const int d = d0 + tid + kCombThreads * c;
-            if (d < D) {
-                if (kFinal) out_O[(int64_t)row * D + d] = (o[c] / l - kr[d]) * inv_T;
-                else out_O[(int64_t)row * D + d] = o[c];
+            const int d = 4 * lane + 128 * c;
+            if (d0 + d < D) *reinterpret_cast<float4*>(&s_o[warp][d]) = o[c];
+        }
+        __syncthreads();
+        for (int d = tid; d < kCombMaxD && d0 + d < D; d += kCombThreads) {
+            const float ov = (s_o[0][d] + s_o[1][d]) + (s_o[2][d] + s_o[3][d]);
+            if (kFinal) {
+                const float kv = round_bf16 ? bf16_round(kr[d0 + d]) : kr[d0 + d];
+                out_O[(int64_t)row * D + d0 + d] = ((ov + wpos * kv) / l_tot - kv) * inv_T * dq_scale;
+            } else {
+                out_O[(int64_t)row * D + d0 + d] = ov;
             }
         }
     }
     if (tid == 0) {
         if (kFinal) {
-            out_a[row] = logf(l_part) + mstar - pos;
+            out_a[row] = logf(l_tot) + mstar - pos;
             pos_is_max[row] = (pos >= mtrue) ? 1 : 0;
             if (out_b) out_b[row] = fmaxf(pos, mtrue);
         } else {
-            out_a[row] = mref; out_b[row] = l_part; out_c[row] = mtrue;
+            out_a[row] = mref; out_b[row] = l_tot; out_c[row] = mtrue;
         }
+    }
+}
+
+// loss = mean(rows), acc = 100 * mean(pos_is_max): one block, deterministic order
+__global__ void __launch_bounds__(256)
+nce_finalize_kernel(const float* __restrict__ rows, const int32_t* __restrict__ pim, int B,
+                    float* __restrict__ loss_mean, float* __restrict__ acc_pct) {
+    __shared__ float r1[8], r2[8];
+    float s = 0.f, c = 0.f;
+    for (int i = threadIdx.x; i < B; i += 256) { s += rows[i]; c += (float)pim[i]; }
+    s = warp_sum(s); c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = s; r2[threadIdx.x >> 5] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float ts = 0.f, tc = 0.f;
+        for (int i = 0; i < 8; ++i) { ts += r1[i]; tc += r2[i]; }
+        *loss_mean = ts / (float)B;
+        *acc_pct = tc * (100.0f / (float)B);
     }
 }
 
@@ -420,16 +455,23 @@ extern "C" __attribute__((visibility("default"))) int moma_nce_partial(const voi
 extern "C" __attribute__((visibility("default"))) int moma_nce_combine(const float* part_m, const float* part_l, const float* part_mmax,
                                 const float* part_O, int n_parts, const float* q_f32,
                                 const float* kpos_f32, int64_t B, int64_t D, float inv_T,
-                                float* loss_rows, float* dq_unit, int32_t* pos_is_max,
-                                float* max_logit, moma_stream_t stream) {
+                                int round_bf16, float dq_scale, float* loss_rows, float* dq_unit,
+                                int32_t* pos_is_max, float* max_logit, float* loss_mean, float* acc_pct,
+                                moma_stream_t stream) {
     MOMA_REQUIRE(B > 0 && D > 0 && n_parts > 0, MOMA_ERR_INVALID, "nce_combine: bad shape");
     MOMA_REQUIRE(part_m && part_l && part_mmax && part_O && q_f32 && kpos_f32 && loss_rows && dq_unit && pos_is_max,
                  MOMA_ERR_INVALID, "nce_combine: null pointer");
+    MOMA_REQUIRE(D % 4 == 0 && aligned16(part_O), MOMA_ERR_ALIGN, "nce_combine: D %% 4 != 0 or part_O unaligned");
     nce_reduce_kernel<true><<<(unsigned)B, kCombThreads, 0, as_stream(stream)>>>(
-        part_m, part_l, part_mmax, part_O, n_parts, q_f32, kpos_f32, (int)B, (int)D, inv_T,
+        part_m, part_l, part_mmax, part_O, n_parts, q_f32, kpos_f32, (int)B, (int)D, inv_T, round_bf16, dq_scale,
         loss_rows, dq_unit, pos_is_max, max_logit, nullptr);
     MOMA_CUDA_LAUNCH_CHECK("nce_combine");
     note_launches(1);
+    if (loss_mean && acc_pct) {
+        nce_finalize_kernel<<<1, 256, 0, as_stream(stream)>>>(loss_rows, pos_is_max, (int)B, loss_mean, acc_pct);
+        MOMA_CUDA_LAUNCH_CHECK("nce_finalize");
+        note_launches(1);
+    }
     return MOMA_OK;
 }
 
@@ -439,9 +481,10 @@ extern "C" __attribute__((visibility("default"))) int moma_nce_merge(
     MOMA_REQUIRE(B > 0 && D > 0 && n_parts > 0, MOMA_ERR_INVALID, "nce_merge: bad shape");
     MOMA_REQUIRE(part_m && part_l && part_mmax && part_O && out_m && out_l && out_mmax && out_O,
                  MOMA_ERR_INVALID, "nce_merge: null pointer");
+    MOMA_REQUIRE(D % 4 == 0 && aligned16(part_O), MOMA_ERR_ALIGN, "nce_merge: D %% 4 != 0 or part_O unaligned");
     nce_reduce_kernel<false><<<(unsigned)B, kCombThreads, 0, as_stream(stream)>>>(
-        part_m, part_l, part_mmax, part_O, n_parts, nullptr, nullptr, (int)B, (int)D, 1.f, out_m, out_O, nullptr,
-        out_l, out_mmax);
+        part_m, part_l, part_mmax, part_O, n_parts, nullptr, nullptr, (int)B, (int)D, 1.f, 0, 1.f, out_m, out_O,
+        nullptr, out_l, out_mmax);
     MOMA_CUDA_LAUNCH_CHECK("nce_merge");
     note_launches(1);
     return MOMA_OK;

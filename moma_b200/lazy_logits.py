@@ -26,12 +26,14 @@ class LazyLogits(torch.Tensor):
     """A [B, K+1] (or [K+1] when B == 1, the reference's .squeeze()) tensor that is not stored."""
 
     @staticmethod
-    def __new__(cls, shape, device, rows, pos_is_max, max_logit, labels, materialize):
+    def __new__(cls, shape, device, nce, labels, materialize):
         t = torch.Tensor._make_wrapper_subclass(cls, tuple(shape), dtype=torch.float32, device=device,
                                                 requires_grad=False)
-        t._rows = rows                      # [B] loss rows, differentiable w.r.t. q
-        t._pos_is_max = pos_is_max          # [B] int32
-        t._max_logit = max_logit            # callable -> [B] max logit per row (for topk values)
+        t._loss = nce.loss                  # [] mean of the loss rows, differentiable w.r.t. q
+        t._rows = nce.rows                  # [B] loss rows, differentiable w.r.t. q
+        t._pos_is_max = nce.pos_is_max      # [B] int32
+        t._max_logit = nce.max_logit        # [B] max logit per row (for topk values)
+        t._acc = nce.acc                    # [1] 100 * mean(pos_is_max)
         t._labels = labels                  # the all-zero labels returned with this handle
         t._materialize = materialize        # callable -> dense [B, K+1] tensor
         t._dense = None
@@ -52,6 +54,11 @@ class LazyLogits(torch.Tensor):
     def pos_is_max(self) -> torch.Tensor:
         return self._pos_is_max
 
+    @property
+    def top1_accuracy(self) -> torch.Tensor:
+        """[1] tensor, 100 * mean(argmax == 0): learning/util.py:25-41 for the all-zero labels."""
+        return self._acc
+
     def _targets_are_zero(self, target) -> bool:
         # the labels tensor handed out together with this handle is all zeros by construction
         return target is self._labels
@@ -62,7 +69,7 @@ class LazyLogits(torch.Tensor):
                 or not self._targets_are_zero(target) or reduction not in ("mean", "sum", "none")):
             return None
         if reduction == "mean":
-            return self._rows.mean()
+            return self._loss
         if reduction == "sum":
             return self._rows.sum()
         return self._rows
@@ -73,7 +80,7 @@ class LazyLogits(torch.Tensor):
         # index 0 where the positive wins; otherwise the winning negative's column is not
         # tracked by the fused kernel and reported as -1 (never equal to a valid label)
         idx = torch.where(self._pos_is_max.bool(), 0, -1).to(torch.int64).unsqueeze(1)
-        return torch.return_types.topk((self._max_logit().unsqueeze(1), idx))
+        return torch.return_types.topk((self._max_logit.unsqueeze(1), idx))
 
     # ---------------------------------------------------------------- dispatch
     @classmethod

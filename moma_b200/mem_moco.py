@@ -112,15 +112,12 @@ class BaseMoCo(nn.Module):
             return self._compute_logit(q, k, queue)          # dense escape hatch (e.g. D = 1280, 2048)
         precision = ops.get_precision()
         shadow = self._shadow_of(queue) if precision == "bf16" and ops.bf16_supported(D) else None
-        rows, pim, mx = ops.nce_rows(q, k, queue, shadow, self.T, precision)
+        nce = ops.nce_rows(q, k, queue, shadow, self.T, precision)
         T = self.T
         # rows about to be overwritten by this step's enqueue: keep them so a late
         # materialisation still sees the pre-enqueue queue (the reference's clone, :89)
         state = {"index": self.index, "saved": None}
         q_d, k_d = q.detach(), k.detach()
-
-        def max_logit():
-            return mx
 
         def materialize():
             src = shadow if shadow is not None else queue
@@ -132,7 +129,7 @@ class BaseMoCo(nn.Module):
             return dense.squeeze().contiguous()
 
         shape = (bsz, K + 1) if bsz != 1 else (K + 1,)
-        handle = LazyLogits(shape, q.device, rows, pim, max_logit, labels, materialize)
+        handle = LazyLogits(shape, q.device, nce, labels, materialize)
         handle._enqueue_state = state
         return handle
 

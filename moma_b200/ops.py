@@ -182,9 +182,11 @@ def nce_partial(q: torch.Tensor, queue: torch.Tensor, inv_T: float, dtype: int, 
     return stats, O
 
 
-def nce_combine(stats: torch.Tensor, O: torch.Tensor, q_f32: torch.Tensor, k_f32: torch.Tensor, inv_T: float):
+def nce_combine(stats: torch.Tensor, O: torch.Tensor, q_f32: torch.Tensor, k_f32: torch.Tensor, inv_T: float,
+                round_bf16: bool = False, dq_scale: float = 1.0, want_mean: bool = False):
     """Merge partials (+ positive column) ->
-    (loss_rows [B], dq_unit [B, D], pos_is_max [B] int32, max_logit [B])."""
+    (loss_rows [B], dq [B, D] (= dq_unit * dq_scale), pos_is_max [B] int32, max_logit [B],
+     loss_mean [] and acc_pct [1] when want_mean)."""
     n_parts, B = stats.shape[1], stats.shape[2]
     D = O.shape[2]
     dev = q_f32.device
@@ -192,8 +194,13 @@ def nce_combine(stats: torch.Tensor, O: torch.Tensor, q_f32: torch.Tensor, k_f32
     dq = torch.empty((B, D), dtype=torch.float32, device=dev)
     pim = torch.empty(B, dtype=torch.int32, device=dev)
     mx = torch.empty(B, dtype=torch.float32, device=dev)
+    fin = torch.empty(2, dtype=torch.float32, device=dev) if want_mean else None
     check(_lib.load().moma_nce_combine(_p(stats[0]), _p(stats[1]), _p(stats[2]), _p(O), n_parts, _p(q_f32),
-                                       _p(k_f32), B, D, inv_T, _p(rows), _p(dq), _p(pim), _p(mx), _stream()))
+                                       _p(k_f32), B, D, inv_T, int(round_bf16), float(dq_scale), _p(rows), _p(dq),
+                                       _p(pim), _p(mx), _p(fin), None if fin is None else fin.data_ptr() + 4,
+                                       _stream()))
+    if want_mean:
+        return rows, dq, pim, mx, fin[0], fin[1:2]
     return rows, dq, pim, mx
 
 
@@ -211,45 +218,71 @@ def nce_merge(stats: torch.Tensor, O: torch.Tensor):
 
 
 def nce_operands(q: torch.Tensor, k: torch.Tensor, precision: str):
-    """Operands in the arithmetic type of the chosen mode: (q_op, dtype, q_f32, k_f32).
-    In bf16 mode q/k are rounded to bf16 (the fp32 copies hold the rounded values)."""
+    """Operands of the chosen mode: (q_op, dtype, q_f32, k_f32, round_bf16).  In bf16 mode the
+    partial kernel reads a bf16 copy of q; the combine kernel rounds q / k inline (round_bf16)."""
     q32, k32 = _f32c(q.detach()), _f32c(k.detach())
     if precision == "bf16":
-        qb = q32.to(torch.bfloat16)
-        return qb, BF16, qb.float(), k32.to(torch.bfloat16).float()
-    return q32, F32, q32, k32
+        qb = torch.empty(q32.shape, dtype=torch.bfloat16, device=q32.device)
+        cast_bf16(q32, qb)
+        return qb, BF16, q32, k32, True
+    return q32, F32, q32, k32, False
+
+
+class NceOut:
+    """Results of one fused InfoNCE pass."""
+    __slots__ = ("loss", "rows", "pos_is_max", "max_logit", "acc")
+
+    def __init__(self, loss, rows, pos_is_max, max_logit, acc):
+        self.loss, self.rows, self.pos_is_max, self.max_logit, self.acc = loss, rows, pos_is_max, max_logit, acc
 
 
 class _NceFused(torch.autograd.Function):
-    """rows[i] = LSE_i - l_i0 and, from the same pass over the queue, d rows[i] / d q_i."""
+    """loss = mean_i(LSE_i - l_i0) (and the per-row terms) with, from the SAME pass over the queue,
+    d loss / d q.  ``compute(q, k)`` runs the kernels (single GPU or sharded) and returns
+    (loss_mean, rows, pos_is_max, max_logit, acc_pct, dq_mean) with dq_mean = d loss_mean / d q."""
 
     @staticmethod
-    def forward(ctx, q, k, queue_f32, queue_bf16, T, precision):
-        inv_T = 1.0 / T
-        q_op, dtype, q32, k32 = nce_operands(q, k, precision)
-        queue = queue_bf16 if dtype == BF16 else queue_f32
-        stats, O = nce_partial(q_op, queue, inv_T, dtype)
-        rows, dq_unit, pim, mx = nce_combine(stats, O, q32, k32, inv_T)
-        ctx.save_for_backward(dq_unit)
-        ctx.q_dtype = q.dtype
-        ctx.mark_non_differentiable(pim, mx)
-        return rows, pim, mx
+    def forward(ctx, q, k, compute):
+        loss, rows, pim, mx, acc, dq_mean = compute(q, k)
+        ctx.save_for_backward(dq_mean)
+        ctx.q_dtype, ctx.B = q.dtype, q.shape[0]
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(pim, mx, acc)
+        return loss, rows, pim, mx, acc
 
     @staticmethod
-    def backward(ctx, g, _gp, _gm):
-        (dq_unit,) = ctx.saved_tensors
-        return (g.unsqueeze(1) * dq_unit).to(ctx.q_dtype), None, None, None, None, None
+    def backward(ctx, g_loss, g_rows, *unused):
+        (dq_mean,) = ctx.saved_tensors
+        grad = None
+        if g_loss is not None:
+            grad = dq_mean * g_loss
+        if g_rows is not None:
+            gr = (g_rows.unsqueeze(1) * dq_mean) * float(ctx.B)
+            grad = gr if grad is None else grad + gr
+        return (None if grad is None else grad.to(ctx.q_dtype)), None, None
+
+
+def nce_fused(q: torch.Tensor, k: torch.Tensor, compute) -> NceOut:
+    return NceOut(*_NceFused.apply(q, k.detach(), compute))
 
 
 def nce_rows(q: torch.Tensor, k: torch.Tensor, queue_f32: torch.Tensor, queue_bf16: Optional[torch.Tensor],
-             T: float, precision: Optional[str] = None):
-    """Single-GPU fused InfoNCE: returns (rows [B] differentiable w.r.t. q, pos_is_max [B] int32,
-    max_logit [B])."""
+             T: float, precision: Optional[str] = None) -> NceOut:
+    """Single-GPU fused InfoNCE over a replicated queue."""
     _need_cuda(q, k, queue_f32)
     precision = precision or _PRECISION
     if precision == "bf16" and (queue_bf16 is None or not bf16_supported(q.shape[1])):
         precision = "fp32"
-    return _NceFused.apply(q, k.detach(), queue_f32, queue_bf16, float(T), precision)
+    inv_T = 1.0 / float(T)
+
+    def compute(q_, k_):
+        q_op, dtype, q32, k32, rnd = nce_operands(q_, k_, precision)
+        queue = queue_bf16 if dtype == BF16 else queue_f32
+        stats, O = nce_partial(q_op, queue, inv_T, dtype)
+        rows, dq, pim, mx, loss, acc = nce_combine(stats, O, q32, k32, inv_T, rnd, 1.0 / q_.shape[0], want_mean=True)
+        return loss, rows, pim, mx, acc, dq
+
+    return nce_fused(q, k, compute)
 
 
 def bf16_supported(D: int) -> bool:

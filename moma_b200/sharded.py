@@ -116,25 +116,31 @@ class ShardedMoCo(BaseMoCo):
         shadow = self._shadow_of(self.memory_shard) if use_bf16 else None
         inv_T = 1.0 / self.T
 
-        q_op, dtype, q32, k32 = ops.nce_operands(q, k, "bf16" if use_bf16 else "fp32")
-        # 1. all-gather the queries (every rank must contribute the same B_local)
-        all_q = torch.empty((W * bsz, D), dtype=q_op.dtype, device=q.device)
-        dist.all_gather_into_tensor(all_q, q_op.contiguous(), group=self.group)
-        # 2. local pass over this rank's K / W rows for all n queries, then fold the splits
-        queue = shadow if use_bf16 else self.memory_shard
-        stats, Opart = ops.nce_partial(all_q, queue, inv_T, dtype)
-        stats, Opart = ops.nce_merge(stats, Opart)                  # [3, 1, n], [1, n, D]
-        # 3. exchange: pack (O | m | l | mmax) per row, route rows to their owner rank
-        packed = torch.cat([Opart[0], stats[:, 0].t()], dim=1).view(W, bsz, D + 3)
-        recv = self._exchange(packed)                               # [W(src), bsz, D + 3]
-        O_all = recv[:, :, :D].contiguous()
-        st_all = recv[:, :, D:].permute(2, 0, 1).contiguous()       # [3, W, bsz]
-        # 4. combine with the positive column
-        rows, dq_unit, pim, mx = ops.nce_combine(st_all, O_all, q32, k32, inv_T)
-        if q.requires_grad and torch.is_grad_enabled():
-            rows = _RowsWithGrad.apply(q, rows, dq_unit)
+        group, rank = self.group, self.rank
+        memory_shard = self.memory_shard
+
+        def compute(q_, k_):
+            q_op, dtype, q32, k32, rnd = ops.nce_operands(q_, k_, "bf16" if use_bf16 else "fp32")
+            # 1. all-gather the queries (every rank must contribute the same B_local)
+            all_q = torch.empty((W * bsz, D), dtype=q_op.dtype, device=q_.device)
+            dist.all_gather_into_tensor(all_q, q_op.contiguous(), group=group)
+            # 2. local pass over this rank's K / W rows for all n queries, then fold the splits
+            queue = shadow if use_bf16 else memory_shard
+            stats, Opart = ops.nce_partial(all_q, queue, inv_T, dtype)
+            stats, Opart = ops.nce_merge(stats, Opart)                  # [3, 1, n], [1, n, D]
+            # 3. exchange: pack (O | m | l | mmax) per row, route rows to their owner rank
+            packed = torch.cat([Opart[0], stats[:, 0].t()], dim=1).view(W, bsz, D + 3)
+            recv = self._exchange(packed)                               # [W(src), bsz, D + 3]
+            O_all = recv[:, :, :D].contiguous()
+            st_all = recv[:, :, D:].permute(2, 0, 1).contiguous()       # [3, W, bsz]
+            # 4. combine with the positive column
+            rows, dq, pim, mx, loss, acc = ops.nce_combine(st_all, O_all, q32, k32, inv_T, rnd, 1.0 / bsz,
+                                                           want_mean=True)
+            return loss, rows, pim, mx, acc, dq
+
+        nce = ops.nce_fused(q, k, compute)
         shape = (bsz, self.K + 1) if bsz != 1 else (self.K + 1,)
-        logits = LazyLogits(shape, q.device, rows, pim, lambda: mx, labels, _stale_after_enqueue)
+        logits = LazyLogits(shape, q.device, nce, labels, _stale_after_enqueue)
         # 5. enqueue the rows this rank owns
         all_k = all_k if all_k is not None else k
         with torch.no_grad():
@@ -144,16 +150,3 @@ class ShardedMoCo(BaseMoCo):
                         self.K, self.index, rank=self.rank, world=W, index_dev=self._index_dev)
         self._update_pointer(all_k.size(0))
         return logits, labels
-
-
-class _RowsWithGrad(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, q, rows, dq_unit):
-        ctx.save_for_backward(dq_unit)
-        ctx.q_dtype = q.dtype
-        return rows.clone()
-
-    @staticmethod
-    def backward(ctx, g):
-        (dq_unit,) = ctx.saved_tensors
-        return (g.unsqueeze(1) * dq_unit).to(ctx.q_dtype), None, None

@@ -38,13 +38,16 @@ def _install_oracle_backend():
         out_s = torch.stack([mref, (w * l).sum(0), mm.max(0).values]).unsqueeze(1).float()
         return out_s, (w.unsqueeze(-1) * O_).sum(0, keepdim=True).float()
 
-    def nce_combine(stats, Op, q32, k32, inv_T):
+    def nce_combine(stats, Op, q32, k32, inv_T, round_bf16=False, dq_scale=1.0, want_mean=False):
         parts = [(stats[0, s].double().numpy(), stats[1, s].double().numpy(), Op[s].double().numpy())
                  for s in range(stats.shape[1])]
         rows, dq, pim = O.nce_merge(parts, q32.double().numpy(), k32.double().numpy(), 1.0 / inv_T)
         mx = np.maximum(stats[2].double().numpy().max(0), (q32.double().numpy() * k32.double().numpy()).sum(1) * inv_T)
-        return (torch.from_numpy(rows).float(), torch.from_numpy(dq).float(),
-                torch.from_numpy(pim.astype(np.int32)), torch.from_numpy(mx).float())
+        out = (torch.from_numpy(rows).float(), torch.from_numpy(dq * dq_scale).float(),
+               torch.from_numpy(pim.astype(np.int32)), torch.from_numpy(mx).float())
+        if want_mean:
+            out += (torch.tensor(rows.mean(), dtype=torch.float32), torch.tensor([pim.mean() * 100.0], dtype=torch.float32))
+        return out
 
     def enqueue(keys, queue, shadow, K, index, rank=0, world=1, normalize=False, eps=1e-12, index_dev=None):
         ids = O.enqueue_ids(keys.shape[0], index, K)
