@@ -23,6 +23,7 @@
 // by more than 2^8), and tracks the true max separately for the top-1 flag.
 #include <cuda.h>
 #include <math_constants.h>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 #include "common.cuh"
@@ -33,7 +34,7 @@ namespace tc {
 constexpr int kBM = 128;          // query rows per M-tile (UMMA M)
 constexpr int kStages = 4;        // queue-tile ring depth
 constexpr int kTmemCols = 512;
-constexpr float kLazyTau = 8.0f;  // log2 units
+constexpr float kLazyTau = 20.0f; // log2 units: P <= 2^20, far inside fp32 / bf16 range; rescales become rare
 
 __device__ int g_tc_error = 0;
 
@@ -470,6 +471,314 @@ nce_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     if (warp == 2) tmem_dealloc(tmem, kTmemCols);
 }
 
+// ============================================================================= v2 kernel
+// One 128-row query tile per CTA; the score tile S is double-buffered in TMEM so the tensor pipe runs
+// S(i+1) / S(i+2) while the softmax of tile i is in flight, and the softmax of each tile is split by
+// COLUMNS over two warpgroups (8 warps, two per scheduler, 64 columns per thread):
+//   warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
+//   warps 4-7   softmax half 0 (score columns  0..63, O columns 0..D/2),
+//   warps 8-11  softmax half 1 (score columns 64..127, O columns D/2..D).
+// The two threads that share a row exchange their half-row maxima through shared memory and a
+// 64-thread named barrier, which also orders "partner has read S" before P (aliasing S) is written.
+// Scale / sum use packed f32x2 instructions; an FMA-pipe polynomial exp2 (ex2_poly) is available behind
+// kPolyExp for when the MUFU pipe (16 exp2/clk/SM: 128x128 exps vs 2 x 128x128x128 MACs per tile) becomes the limit.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d)
+        : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)), "l"(*reinterpret_cast<uint64_t*>(&c)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d)
+        : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+// 2^x on the FMA pipe: x = n + f, f in [-0.5, 0.5], cubic minimax for 2^f (max rel. error 7.5e-5, far
+// below the bf16 rounding of P), exponent added as an integer.
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -125.0f);
+    const float magic = 12582912.0f;                      // 1.5 * 2^23: rounds x to the nearest integer
+    const float t = x + magic;
+    const float f = x - (t - magic);
+    float p = fmaf(f, 0.0551716685f, 0.2426111251f);
+    p = fmaf(p, f, 0.6932609677f);
+    p = fmaf(p, f, 0.9999280572f);
+    return __int_as_float(__float_as_int(p) + ((__float_as_int(t) - 0x4B400000) << 23));
+}
+// Measured on B200 (profiles/): with 8 softmax warps the kernel is issue/latency-bound, not MUFU-bound
+// (XU pipe ~31% busy), and the 9-instruction polynomial costs more issue slots than the MUFU op it saves.
+constexpr bool kPolyExp = false;
+__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+struct __align__(8) Bars2 {
+    uint64_t q_full;
+    uint64_t kv_full[kStages];
+    uint64_t kv_empty[kStages];
+    uint64_t s_full[2];
+    uint64_t p_full[2];
+    uint64_t pv_done;
+    uint64_t o_final;
+    uint32_t tmem_base;
+    uint32_t pad;
+    float xch[2][2][kBM];      // [tile parity][half][row] half-row maxima
+    float lsum[kBM];           // half-1 row sums for the epilogue
+};
+
+template <int D>
+struct Cfg2 {
+    static constexpr int BN = 128;
+    static constexpr int KB = D / 64;
+    static constexpr int Q_BLOCK = kBM * 128;
+    static constexpr int Q_TILE = KB * Q_BLOCK;
+    static constexpr int K_BLOCK = BN * 128;
+    static constexpr int K_TILE = KB * K_BLOCK;
+    static constexpr int SMEM_DATA = Q_TILE + kStages * K_TILE;
+    static constexpr int SMEM_TOTAL = SMEM_DATA + 1024 + (int)sizeof(Bars2);
+    static constexpr int THREADS = 384;
+    static constexpr int O_COL = 256;
+    static constexpr int OH = D / 2;          // O columns per softmax half
+    static_assert(256 + D <= kTmemCols && SMEM_TOTAL <= 227 * 1024, "budget");
+};
+
+template <int D>
+__global__ void __launch_bounds__(384, 1)
+nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+               int B, long long K_local, float scale_log2, int n_splits, float* __restrict__ part_m,
+               float* __restrict__ part_l, float* __restrict__ part_mmax, float* __restrict__ part_O,
+               float* __restrict__ dbg_S) {
+    using C = Cfg2<D>;
+    constexpr int BN = C::BN;
+    extern __shared__ uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mt = blockIdx.x, split = blockIdx.y;
+    const int T_total = (int)((K_local + BN - 1) / BN);
+    const int t0 = (int)((long long)T_total * split / n_splits);
+    const int t1 = (int)((long long)T_total * (split + 1) / n_splits);
+    const int nt = t1 - t0;
+    const int row_base = mt * kBM;
+
+    if (nt <= 0) {      // empty split: neutral partials
+        if (warp >= 4 && warp < 8) {
+            const int row = row_base + ((warp & 3) << 5) + lane;
+            if (row < B) {
+                const long long o = (long long)split * B + row;
+                part_m[o] = -CUDART_INF_F; part_mmax[o] = -CUDART_INF_F; part_l[o] = 0.f;
+                for (int d = 0; d < D; ++d) part_O[o * D + d] = 0.f;
+            }
+        }
+        return;
+    }
+
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t q_smem = base;
+    const uint32_t kv_smem = base + C::Q_TILE;
+    Bars2* bars = reinterpret_cast<Bars2*>(smem_raw + (base - raw) + C::SMEM_DATA);
+    const uint32_t b_q_full = smem_u32(&bars->q_full);
+    auto b_kv_full = [&](int s) { return smem_u32(&bars->kv_full[s]); };
+    auto b_kv_empty = [&](int s) { return smem_u32(&bars->kv_empty[s]); };
+    auto b_s_full = [&](int b) { return smem_u32(&bars->s_full[b]); };
+    auto b_p_full = [&](int b) { return smem_u32(&bars->p_full[b]); };
+    const uint32_t b_pv_done = smem_u32(&bars->pv_done);
+    const uint32_t b_o_final = smem_u32(&bars->o_final);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_k);
+        mbar_init(b_q_full, 1);
+        for (int s = 0; s < kStages; ++s) { mbar_init(b_kv_full(s), 1); mbar_init(b_kv_empty(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(b_s_full(b), 1); mbar_init(b_p_full(b), 256); }
+        mbar_init(b_pv_done, 1);
+        mbar_init(b_o_final, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(smem_u32(&bars->tmem_base), kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+    auto s_colf = [&](int b) { return tmem + (uint32_t)(b * 128); };
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            mbar_expect_tx(b_q_full, C::Q_TILE);
+            for (int kb = 0; kb < C::KB; ++kb)
+                tma_load_2d(q_smem + kb * C::Q_BLOCK, &tmap_q, kb * 64, row_base, b_q_full);
+            for (int i = 0; i < nt; ++i) {
+                const int s = i % kStages;
+                mbar_wait(b_kv_empty(s), ((i / kStages) & 1) ^ 1, 301);
+                mbar_expect_tx(b_kv_full(s), C::K_TILE);
+                for (int kb = 0; kb < C::KB; ++kb)
+                    tma_load_2d(kv_smem + s * C::K_TILE + kb * C::K_BLOCK, &tmap_k, kb * 64, (t0 + i) * BN, b_kv_full(s));
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc(kBM, BN, 0, 0);
+            constexpr uint32_t idesc_o = make_idesc(kBM, D, 0, 1);
+            const uint64_t q_desc0 = make_desc(q_smem, 16, 1024);
+            const uint64_t k_desc0 = make_desc(kv_smem, 16, 1024);
+            const uint64_t v_desc0 = make_desc(kv_smem, C::K_BLOCK, 1024);
+            auto issue_s = [&](int b, int stage) {
+                const uint64_t db0 = k_desc0 + (uint64_t)((stage * C::K_TILE) >> 4);
+#pragma unroll 1
+                for (int ks = 0; ks < D / 16; ++ks) {
+                    const uint32_t qoff = (uint32_t)((ks >> 2) * C::Q_BLOCK + (ks & 3) * 32) >> 4;
+                    const uint32_t koff = (uint32_t)((ks >> 2) * C::K_BLOCK + (ks & 3) * 32) >> 4;
+                    umma_ss(s_colf(b), q_desc0 + qoff, db0 + koff, idesc_s, ks > 0 ? 1u : 0u);
+                }
+                umma_commit(b_s_full(b));
+            };
+            auto issue_pv = [&](int b, int stage, bool accumulate) {
+                const uint64_t db0 = v_desc0 + (uint64_t)((stage * C::K_TILE) >> 4);
+#pragma unroll 1
+                for (int ks = 0; ks < BN / 16; ++ks)
+                    umma_ts(tmem + C::O_COL, s_colf(b) + ks * 8, db0 + (uint64_t)(ks * (2048 >> 4)), idesc_o,
+                            (accumulate || ks > 0) ? 1u : 0u);
+                umma_commit(b_pv_done);
+            };
+            mbar_wait(b_q_full, 0, 302);
+            mbar_wait(b_kv_full(0), 0, 303);
+            tc_fence_after();
+            issue_s(0, 0);
+            if (nt > 1) { mbar_wait(b_kv_full(1), 0, 306); tc_fence_after(); issue_s(1, 1); }
+            for (int i = 0; i < nt; ++i) {
+                const int st = i % kStages, b = i & 1;
+                mbar_wait(b_p_full(b), (i >> 1) & 1, 304);
+                tc_fence_after();
+                issue_pv(b, st, i > 0);
+                umma_commit(b_kv_empty(st));
+                if (i + 2 < nt) {
+                    const int sn = (i + 2) % kStages;
+                    mbar_wait(b_kv_full(sn), ((i + 2) / kStages) & 1, 305);
+                    tc_fence_after();
+                    issue_s(b, sn);
+                }
+            }
+            umma_commit(b_o_final);
+        }
+    } else if (warp >= 4) {
+        // ===================================================== softmax (two column halves)
+        const int half = (warp - 4) >> 2;
+        const int wq = warp & 3;
+        const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+        const int rit = wq * 32 + lane;                       // row in tile
+        const int row = row_base + rit;
+        const uint32_t o_addr = tmem + lane_off + C::O_COL + half * C::OH;
+        float m_ref = -CUDART_INF_F, m_true = -CUDART_INF_F;
+        float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);     // running half-row sums
+        const bool ragged_last = (K_local % BN) != 0;
+        const float2 sc2 = make_float2(scale_log2, scale_log2);
+
+        for (int i = 0; i < nt; ++i) {
+            const int b = i & 1;
+            mbar_wait(b_s_full(b), (i >> 1) & 1, 401);
+            tc_fence_after();
+            uint32_t v[64];
+            {
+                uint32_t* v0 = v; uint32_t* v1 = v + 32;
+                TMEM_LD32(s_colf(b) + lane_off + half * 64, v0);
+                TMEM_LD32(s_colf(b) + lane_off + half * 64 + 32, v1);
+            }
+            tmem_wait_ld();
+            if (dbg_S != nullptr && i == 0 && split == 0 && row < B) {
+#pragma unroll
+                for (int j = 0; j < 64; ++j) dbg_S[(long long)row * BN + half * 64 + j] = __uint_as_float(v[j]);
+            }
+            if (ragged_last && (t0 + i) == T_total - 1) {
+                const int valid = (int)(K_local - (long long)(T_total - 1) * BN) - half * 64;
+#pragma unroll
+                for (int j = 0; j < 64; ++j)
+                    if (j >= valid) v[j] = __float_as_uint(-CUDART_INF_F);
+            }
+            float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
+#pragma unroll
+            for (int j = 0; j < 64; j += 4) {
+                mx0 = fmaxf(fmaxf(mx0, __uint_as_float(v[j])), __uint_as_float(v[j + 1]));
+                mx1 = fmaxf(fmaxf(mx1, __uint_as_float(v[j + 2])), __uint_as_float(v[j + 3]));
+            }
+            // exchange the half-row maxima with the thread holding the other 64 columns of this row
+            bars->xch[i & 1][half][rit] = fmaxf(mx0, mx1);
+            pair_barrier(1 + wq);
+            const float mx = fmaxf(fmaxf(mx0, mx1), bars->xch[i & 1][half ^ 1][rit]) * scale_log2;
+            m_true = fmaxf(m_true, mx);
+            const bool need = mx > m_ref + kLazyTau;                 // identical in both halves of the row
+            if (i > 0 && __any_sync(0xffffffffu, need)) {
+                mbar_wait(b_pv_done, (i - 1) & 1, 402);
+                tc_fence_after();
+                const float f = need ? ex2(m_ref - mx) : 1.0f;
+#pragma unroll 1
+                for (int c = 0; c < C::OH / 32; ++c) {
+                    uint32_t o[32];
+                    TMEM_LD32(o_addr + 32 * c, o);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * f);
+                    TMEM_ST32(o_addr + 32 * c, o);
+                }
+                tmem_wait_st();
+                l2a.x *= f; l2a.y *= f; l2b.x *= f; l2b.y *= f;
+            }
+            if (need) m_ref = mx;
+            const float2 ng2 = make_float2(-m_ref, -m_ref);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float2 x01 = ffma2(make_float2(__uint_as_float(v[32 * c + j]), __uint_as_float(v[32 * c + j + 1])), sc2, ng2);
+                    const float2 x23 = ffma2(make_float2(__uint_as_float(v[32 * c + j + 2]), __uint_as_float(v[32 * c + j + 3])), sc2, ng2);
+                    const float2 p01 = make_float2(ex2(x01.x), ex2(x01.y));
+                    const float2 p23 = make_float2(ex2(x23.x), kPolyExp ? ex2_poly(x23.y) : ex2(x23.y));
+                    l2a = fadd2(l2a, p01);
+                    l2b = fadd2(l2b, p23);
+                    pk[j >> 1] = pack_bf16(p01.x, p01.y);
+                    pk[(j >> 1) + 1] = pack_bf16(p23.x, p23.y);
+                }
+                // P (bf16 pairs) aliases the S buffer: half h owns packed columns [32h, 32h + 32)
+                TMEM_ST16(s_colf(b) + lane_off + half * 32 + 16 * c, pk);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(b_p_full(b));
+        }
+
+        // epilogue: O (TMEM) -> part_O (each half writes its D/2 columns), stats by half 0
+        const float l_half = (l2a.x + l2a.y) + (l2b.x + l2b.y);
+        if (half == 1) bars->lsum[rit] = l_half;
+        mbar_wait(b_o_final, 0, 403);
+        tc_fence_after();
+        const long long orow = (long long)split * B + row;
+#pragma unroll 1
+        for (int c = 0; c < C::OH / 32; ++c) {
+            uint32_t o[32];
+            TMEM_LD32(o_addr + 32 * c, o);
+            tmem_wait_ld();
+            if (row < B) {
+                float4* dst = reinterpret_cast<float4*>(part_O + orow * D + half * C::OH + 32 * c);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    dst[j] = make_float4(__uint_as_float(o[4 * j]), __uint_as_float(o[4 * j + 1]),
+                                         __uint_as_float(o[4 * j + 2]), __uint_as_float(o[4 * j + 3]));
+            }
+        }
+        pair_barrier(1 + wq);
+        if (half == 0 && row < B) {
+            constexpr float kLn2 = 0.6931471805599453f;
+            part_m[orow] = m_ref * kLn2;
+            part_mmax[orow] = m_true * kLn2;
+            part_l[orow] = l_half + bars->lsum[rit];
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem, kTmemCols);
+}
+
 // ----------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -527,9 +836,37 @@ static int cached_map(CUtensorMap* out, const void* ptr, long long rows, int D, 
     return MOMA_OK;
 }
 
+static bool use_v2(int64_t D) {
+    static const bool force_v1 = getenv("MOMA_B200_NCE_V1") != nullptr;
+    return !force_v1 && (D == 64 || D == 128);
+}
 static void pick(int64_t B, int64_t D, int* nq, int* bn) {
-    *nq = (D == 256 || B <= kBM) ? 1 : 2;
+    *nq = (use_v2(D) || D == 256 || B <= kBM) ? 1 : 2;
     *bn = (D == 256) ? 64 : 128;
+}
+
+template <int D>
+static int launch2(const void* q, const void* queue, int64_t B, int64_t K_local, float inv_T, int n_splits,
+                   float* pm, float* pl, float* pmm, float* pO, float* dbg, cudaStream_t st) {
+    using C = Cfg2<D>;
+    CUtensorMap mq, mk;
+    int rc = cached_map(&mq, q, B, D, kBM);
+    if (rc != MOMA_OK) return rc;
+    rc = cached_map(&mk, queue, K_local, D, C::BN);
+    if (rc != MOMA_OK) return rc;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(nce_tc2_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_TOTAL);
+        MOMA_REQUIRE(e == cudaSuccess, MOMA_ERR_CUDA, "nce_tc2: smem attribute: %s", cudaGetErrorString(e));
+        attr = true;
+    }
+    const dim3 grid((unsigned)((B + kBM - 1) / kBM), (unsigned)n_splits);
+    const float scale_log2 = inv_T * 1.4426950408889634f;
+    nce_tc2_kernel<D><<<grid, C::THREADS, C::SMEM_TOTAL, st>>>(mq, mk, (int)B, (long long)K_local, scale_log2, n_splits,
+                                                              pm, pl, pmm, pO, dbg);
+    MOMA_CUDA_LAUNCH_CHECK("nce_partial(bf16/tcgen05 v2)");
+    note_launches(1);
+    return MOMA_OK;
 }
 
 template <int D, int NQ, int BN>
@@ -563,6 +900,10 @@ static int dispatch(const void* q, const void* queue, int64_t B, int64_t D, int6
                  MOMA_ERR_ALIGN, "nce_tc: q / queue must be 128-byte aligned for TMA");
     int nq, bn;
     pick(B, D, &nq, &bn);
+    if (use_v2(D)) {
+        if (D == 64) return launch2<64>(q, queue, B, K_local, inv_T, n_splits, pm, pl, pmm, pO, dbg, st);
+        return launch2<128>(q, queue, B, K_local, inv_T, n_splits, pm, pl, pmm, pO, dbg, st);
+    }
     if (D == 64) return nq == 2 ? launch<64, 2, 128>(q, queue, B, K_local, inv_T, n_splits, pm, pl, pmm, pO, dbg, st)
                                 : launch<64, 1, 128>(q, queue, B, K_local, inv_T, n_splits, pm, pl, pmm, pO, dbg, st);
     if (D == 128) return nq == 2 ? launch<128, 2, 128>(q, queue, B, K_local, inv_T, n_splits, pm, pl, pmm, pO, dbg, st)

@@ -10,8 +10,8 @@ dev = torch.device("cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
-def time_kernel(B, D, K, splits=None, cold=True, reps=15):
-    q = torch.randn(B, D, device=dev).to(torch.bfloat16)
+def time_kernel(B, D, K, splits=None, cold=True, reps=15, qscale=1.0):
+    q = (torch.randn(B, D, device=dev) * qscale).to(torch.bfloat16)
     queue = torch.nn.functional.normalize(torch.randn(K, D, device=dev)).to(torch.bfloat16)
     if splits is None:
         splits = lib.moma_nce_num_splits(B, D, K, BF16)
@@ -36,12 +36,13 @@ def time_kernel(B, D, K, splits=None, cold=True, reps=15):
 
 if __name__ == "__main__":
     print("B D K splits tiles/cta us(cold) us(warm) TFLOP/s(cold)")
+    qscale = float(os.environ.get("QSCALE", "1.0"))
     for (B, D, K) in [(512, 128, 16384), (512, 128, 65536), (512, 128, 262144), (512, 128, 1048576),
                       (256, 128, 16384), (256, 128, 65536), (1024, 128, 65536), (1024, 256, 131072), (512, 64, 65536)]:
-        for splits in ([None] if K > 65536 else [None, 37, 18]):
+        for splits in [None]:
             try:
-                us, sp = time_kernel(B, D, K, splits)
-                usw, _ = time_kernel(B, D, K, splits, cold=False)
+                us, sp = time_kernel(B, D, K, splits, qscale=qscale)
+                usw, _ = time_kernel(B, D, K, splits, cold=False, qscale=qscale)
             except Exception as e:
                 print(B, D, K, splits, "ERR", e); continue
             bn = 64 if D == 256 else 128
