@@ -449,3 +449,53 @@ def test_full_size_properties(ops):
         assert idx == start
         want = (torch.arange(K, device="cuda") - start) % K
         assert torch.equal(queue[:, 0].long(), want)
+
+
+# ------------------------------------------------------------- CUDA-graph replay == eager
+def test_graphed_step_matches_eager(ops):
+    """The captured graph (device-resident queue pointer) reproduces the eager step exactly:
+    same losses, gradients, queue contents and pointer over several replays incl. a wrap."""
+    from argparse import Namespace
+    from moma_b200 import CMO, ContrastTrainer, build_mem
+    from moma_b200.graphed import GraphedStep
+
+    def make():
+        torch.manual_seed(3)
+        opt = Namespace(head="mlp", s_dim=32, t_dim=32, feat_dim=64, attn="self", mem="MoCo", nce_k=160, nce_t=0.15)
+        contrast, crit = build_mem(opt).cuda(), CMO(opt).cuda()
+        fs = torch.randn(48, 32, device="cuda", requires_grad=True)
+        ft = torch.randn(48, 32, device="cuda")
+        ce = torch.nn.CrossEntropyLoss()
+
+        def step():
+            ContrastTrainer.momentum_update(crit.embed_s, crit.embed_t, 0.999)
+            with torch.no_grad():
+                k = crit.embed_t(ft)
+            q = crit.atts_q(crit.embed_s(fs)); k2 = crit.atts_k(k); ak = crit.atts_queue(k)
+            logits, labels = contrast(q=q, k=k2, all_k=ak)
+            loss = ce(logits, labels)
+            fs.grad = None
+            for p in crit.parameters():
+                p.grad = None
+            loss.backward()
+            return loss
+        return contrast, crit, fs, step
+
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        c_e, crit_e, fs_e, step_e = make()
+        eager = []
+        for _ in range(3 + 5):                        # GraphedStep warms up 3 times before capturing
+            l = step_e()
+            eager.append((l.item(), fs_e.grad.clone(), c_e.memory.clone(), c_e.index))
+        c_g, crit_g, fs_g, step_g = make()
+        g = GraphedStep(step_g, contrast=c_g, rows_per_step=48, warmup=3)
+        assert c_g.index == eager[2][3]
+        for i in range(5):
+            l = g.replay()
+            torch.cuda.synchronize()
+            want = eager[3 + i]
+            assert abs(l.item() - want[0]) < 1e-6 * abs(want[0])
+            assert torch.allclose(fs_g.grad, want[1], rtol=1e-5, atol=1e-8)
+            assert torch.equal(c_g.memory, want[2]) and c_g.index == want[3]
+        assert c_g.index == (8 * 48) % 160                                   # wrapped twice
