@@ -219,7 +219,16 @@ def run_ours(args, cfg, rank, world, local_rank):
     except Exception:
         pass
 
-    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    # L2 flush between steps: READ a 256 MiB buffer (leaves the 126 MB L2 full of clean foreign lines; a
+    # write-flush would leave it dirty and charge the write-back to the next kernel)
+    flush_buf = None if args.no_flush else torch.empty(64 << 20, dtype=torch.int32, device=device).zero_()
+    flush_out = torch.zeros(1, dtype=torch.int64, device=device)
+
+    class _Flush:
+        @staticmethod
+        def fill_(_v):
+            torch.sum(flush_buf, dim=(0,), keepdim=True, out=flush_out)
+    flush = None if args.no_flush else _Flush
 
     def barrier():
         if world > 1:
@@ -336,7 +345,7 @@ def run_ours(args, cfg, rank, world, local_rank):
                    "s_dim": cfg["s_dim"], "t_dim": cfg["t_dim"], "heads": cfg["H"], "nce_t": T_NCE, "alpha": ALPHA,
                    "head": "mlp", "attn": "self", "ema_pair": "ResNet-18 student -> ResNet-18 momentum twin (11.18M)",
                    "queue": "replicated" if world == 1 else f"sharded by K over {world} ranks (cyclic)",
-                   "l2": "no flush" if args.no_flush else "L2 flushed (256 MiB write) before every step; per-step CUDA events summed",
+                   "l2": "no flush" if args.no_flush else "L2 flushed (256 MiB read) before every step; per-step CUDA events summed",
                    "timed_region": "EMA + heads + 3x attention + fused InfoNCE/CE fwd+bwd + enqueue (criterion step, L1)"},
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": cs.h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms / args.steps,

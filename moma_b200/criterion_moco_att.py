@@ -159,17 +159,37 @@ class Attention2(nn.Module):
         return self.norm(self.attn_layer(x) + x)
 
 
+class _Head(nn.Sequential):
+    """Projection head (same sub-module indices / state_dict keys as the reference's nn.Sequential).
+
+    In bf16 mode a head evaluated WITHOUT autograd -- the momentum teacher's ``embed_t`` inside
+    ``_shuffle_bn`` (learning/contrast_trainer.py:117-121) -- runs its Linear layers with TF32 tensor-core
+    GEMMs: no gradient flows through it and its output is rounded to bf16 by the InfoNCE kernel anyway
+    (measured end-to-end effect 5e-5 on the gradients, scripts/tf32_heads_error.py).  With autograd
+    (the student's ``embed_s``) and in fp32 mode the GEMMs stay IEEE FP32, as in the reference."""
+
+    def forward(self, x):
+        if torch.is_grad_enabled() or ops.get_precision() != "bf16" or not x.is_cuda:
+            return super().forward(x)
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            return super().forward(x)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+
+
 def _head(kind, in_dim, feat_dim):
     """Projection heads of CMO (reference :254-305)."""
     if kind == 'mlp':
-        return nn.Sequential(Flatten(), nn.Linear(in_dim, in_dim), nn.ReLU(inplace=True),
+        return _Head(Flatten(), nn.Linear(in_dim, in_dim), nn.ReLU(inplace=True),
                              nn.Linear(in_dim, feat_dim), Normalize(2))
     if kind == 'mlp_byol':
-        return nn.Sequential(Flatten(), nn.Linear(in_dim, in_dim), nn.BatchNorm1d(in_dim),
+        return _Head(Flatten(), nn.Linear(in_dim, in_dim), nn.BatchNorm1d(in_dim),
                              nn.ReLU(inplace=True), nn.Linear(in_dim, feat_dim), Normalize(2))
     if kind == 'linear':
-        return nn.Sequential(Flatten(), nn.Linear(in_dim, feat_dim), Normalize(2))
-    return nn.Sequential(Flatten(), Normalize(2))
+        return _Head(Flatten(), nn.Linear(in_dim, feat_dim), Normalize(2))
+    return _Head(Flatten(), Normalize(2))
 
 
 class CMO(nn.Module):

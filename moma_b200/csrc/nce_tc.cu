@@ -472,8 +472,8 @@ nce_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 }
 
 // ============================================================================= v2 kernel
-// One 128-row query tile per CTA; the score tile S is double-buffered in TMEM so the tensor pipe runs
-// S(i+1) / S(i+2) while the softmax of tile i is in flight, and the softmax of each tile is split by
+// One 128-row query tile per CTA; the score tile S is triple-buffered in TMEM (S0 S1 S2 O = 512 columns at
+// D = 128) so the tensor pipe has S(i+1), S(i+2) finished while the softmax of tile i is in flight, and the softmax of each tile is split by
 // COLUMNS over two warpgroups (8 warps, two per scheduler, 64 columns per thread):
 //   warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
 //   warps 4-7   softmax half 0 (score columns  0..63, O columns 0..D/2),
@@ -511,13 +511,16 @@ __device__ __forceinline__ float ex2_poly(float x) {
 constexpr bool kPolyExp = false;
 __device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
+constexpr int kStages2 = 5;     // queue-tile ring depth of the v2 kernel
+constexpr int kSBuf = 3;        // score buffers in TMEM: S(i+1), S(i+2) are ready while softmax works on S(i)
+
 struct __align__(8) Bars2 {
     uint64_t q_full;
-    uint64_t kv_full[kStages];
-    uint64_t kv_empty[kStages];
-    uint64_t s_full[2];
-    uint64_t p_full[2];
-    uint64_t pv_done;
+    uint64_t kv_full[kStages2];
+    uint64_t kv_empty[kStages2];
+    uint64_t s_full[kSBuf];
+    uint64_t p_full[kSBuf];
+    uint64_t pv_done[kSBuf];   // PV(i) commits pv_done[i % kSBuf]: a waiter is never more than one phase behind
     uint64_t o_final;
     uint32_t tmem_base;
     uint32_t pad;
@@ -533,12 +536,12 @@ struct Cfg2 {
     static constexpr int Q_TILE = KB * Q_BLOCK;
     static constexpr int K_BLOCK = BN * 128;
     static constexpr int K_TILE = KB * K_BLOCK;
-    static constexpr int SMEM_DATA = Q_TILE + kStages * K_TILE;
+    static constexpr int SMEM_DATA = Q_TILE + kStages2 * K_TILE;
     static constexpr int SMEM_TOTAL = SMEM_DATA + 1024 + (int)sizeof(Bars2);
     static constexpr int THREADS = 384;
-    static constexpr int O_COL = 256;
+    static constexpr int O_COL = 128 * kSBuf;
     static constexpr int OH = D / 2;          // O columns per softmax half
-    static_assert(256 + D <= kTmemCols && SMEM_TOTAL <= 227 * 1024, "budget");
+    static_assert(128 * kSBuf + D <= kTmemCols && SMEM_TOTAL <= 227 * 1024, "budget");
 };
 
 template <int D>
@@ -580,16 +583,15 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     auto b_kv_empty = [&](int s) { return smem_u32(&bars->kv_empty[s]); };
     auto b_s_full = [&](int b) { return smem_u32(&bars->s_full[b]); };
     auto b_p_full = [&](int b) { return smem_u32(&bars->p_full[b]); };
-    const uint32_t b_pv_done = smem_u32(&bars->pv_done);
+    auto b_pv_done = [&](int b) { return smem_u32(&bars->pv_done[b]); };
     const uint32_t b_o_final = smem_u32(&bars->o_final);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_q);
         tma_prefetch_desc(&tmap_k);
         mbar_init(b_q_full, 1);
-        for (int s = 0; s < kStages; ++s) { mbar_init(b_kv_full(s), 1); mbar_init(b_kv_empty(s), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(b_s_full(b), 1); mbar_init(b_p_full(b), 256); }
-        mbar_init(b_pv_done, 1);
+        for (int s = 0; s < kStages2; ++s) { mbar_init(b_kv_full(s), 1); mbar_init(b_kv_empty(s), 1); }
+        for (int b = 0; b < kSBuf; ++b) { mbar_init(b_s_full(b), 1); mbar_init(b_p_full(b), 256); mbar_init(b_pv_done(b), 1); }
         mbar_init(b_o_final, 1);
         fence_barrier_init();
     }
@@ -607,8 +609,8 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             for (int kb = 0; kb < C::KB; ++kb)
                 tma_load_2d(q_smem + kb * C::Q_BLOCK, &tmap_q, kb * 64, row_base, b_q_full);
             for (int i = 0; i < nt; ++i) {
-                const int s = i % kStages;
-                mbar_wait(b_kv_empty(s), ((i / kStages) & 1) ^ 1, 301);
+                const int s = i % kStages2;
+                mbar_wait(b_kv_empty(s), ((i / kStages2) & 1) ^ 1, 301);
                 mbar_expect_tx(b_kv_full(s), C::K_TILE);
                 for (int kb = 0; kb < C::KB; ++kb)
                     tma_load_2d(kv_smem + s * C::K_TILE + kb * C::K_BLOCK, &tmap_k, kb * 64, (t0 + i) * BN, b_kv_full(s));
@@ -638,22 +640,22 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 for (int ks = 0; ks < BN / 16; ++ks)
                     umma_ts(tmem + C::O_COL, s_colf(b) + ks * 8, db0 + (uint64_t)(ks * (2048 >> 4)), idesc_o,
                             (accumulate || ks > 0) ? 1u : 0u);
-                umma_commit(b_pv_done);
+                umma_commit(b_pv_done(b));
             };
             mbar_wait(b_q_full, 0, 302);
             mbar_wait(b_kv_full(0), 0, 303);
             tc_fence_after();
             issue_s(0, 0);
-            if (nt > 1) { mbar_wait(b_kv_full(1), 0, 306); tc_fence_after(); issue_s(1, 1); }
+            for (int j = 1; j < kSBuf && j < nt; ++j) { mbar_wait(b_kv_full(j), 0, 306); tc_fence_after(); issue_s(j, j); }
             for (int i = 0; i < nt; ++i) {
-                const int st = i % kStages, b = i & 1;
-                mbar_wait(b_p_full(b), (i >> 1) & 1, 304);
+                const int st = i % kStages2, b = i % kSBuf;
+                mbar_wait(b_p_full(b), (i / kSBuf) & 1, 304);
                 tc_fence_after();
                 issue_pv(b, st, i > 0);
                 umma_commit(b_kv_empty(st));
-                if (i + 2 < nt) {
-                    const int sn = (i + 2) % kStages;
-                    mbar_wait(b_kv_full(sn), ((i + 2) / kStages) & 1, 305);
+                if (i + kSBuf < nt) {
+                    const int sn = (i + kSBuf) % kStages2;
+                    mbar_wait(b_kv_full(sn), ((i + kSBuf) / kStages2) & 1, 305);
                     tc_fence_after();
                     issue_s(b, sn);
                 }
@@ -674,8 +676,8 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const float2 sc2 = make_float2(scale_log2, scale_log2);
 
         for (int i = 0; i < nt; ++i) {
-            const int b = i & 1;
-            mbar_wait(b_s_full(b), (i >> 1) & 1, 401);
+            const int b = i % kSBuf;
+            mbar_wait(b_s_full(b), (i / kSBuf) & 1, 401);
             tc_fence_after();
             uint32_t v[64];
             {
@@ -707,7 +709,7 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             m_true = fmaxf(m_true, mx);
             const bool need = mx > m_ref + kLazyTau;                 // identical in both halves of the row
             if (i > 0 && __any_sync(0xffffffffu, need)) {
-                mbar_wait(b_pv_done, (i - 1) & 1, 402);
+                mbar_wait(b_pv_done((i - 1) % kSBuf), ((i - 1) / kSBuf) & 1, 402);
                 tc_fence_after();
                 const float f = need ? ex2(m_ref - mx) : 1.0f;
 #pragma unroll 1
