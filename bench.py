@@ -151,11 +151,16 @@ class CriterionStep:
         f_s = crit.embed_s(feat_s)
         f_s = crit.atts_q(f_s)
         k = crit.atts_k(k)
+        if self.world > 1:
+            # K-sharded queue: this rank only enqueues every W-th attended key -> attend those rows only
+            owned = crit.atts_queue.forward_rows(all_k, *self.contrast.owned_rows(all_k.shape[0]))
+            return self._loss_and_backward(f_s, k, None, feat_s, owned_k=owned)
         all_k = crit.atts_queue(all_k)
         return self._loss_and_backward(f_s, k, all_k, feat_s)
 
-    def _loss_and_backward(self, f_s, k, all_k, feat_s):
-        output = self.contrast(q=f_s, k=k, all_k=all_k)
+    def _loss_and_backward(self, f_s, k, all_k, feat_s, owned_k=None):
+        output = self.contrast(q=f_s, k=k, owned_k=owned_k) if owned_k is not None else \
+            self.contrast(q=f_s, k=k, all_k=all_k)
         losses, accs = self.trainer._compute_loss_accuracy(output[:-1], output[-1], self.ce)
         for p in self.params:
             p.grad = None
@@ -184,13 +189,17 @@ class CriterionStep:
                 k0 = crit.embed_t(self.feat_t)
             all_k = self.trainer._global_gather(k0) if self.world > 1 else k0
             s_u.wait_stream(s_t)
+            owned = None
             with torch.cuda.stream(s_u):
-                all_k = crit.atts_queue(all_k)
+                if self.world > 1:
+                    owned = crit.atts_queue.forward_rows(all_k, *self.contrast.owned_rows(all_k.shape[0]))
+                else:
+                    all_k = crit.atts_queue(all_k)
             k = crit.atts_k(k0)
         f_s = crit.embed_s(self.feat_s)
         f_s = crit.atts_q(f_s)
         main.wait_stream(s_t); main.wait_stream(s_u)
-        loss = self._loss_and_backward(f_s, k, all_k, self.feat_s)
+        loss = self._loss_and_backward(f_s, k, all_k, self.feat_s, owned_k=owned)
         main.wait_stream(s_ema)
         return loss
 
@@ -450,12 +459,18 @@ def main():
         return
 
     import torch.distributed as dist
+    # stdout carries exactly one JSON line: everything else any library prints on fd 1 (e.g. NCCL's version
+    # banner) is sent to stderr; the JSON goes to a private duplicate of the original stdout
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world > 1:
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     out = run_ours(args, cfg, rank, world, local_rank)
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        json_out.write(json.dumps(out) + "\n")
+        json_out.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -95,6 +95,11 @@ int moma_l2norm_bwd(const float *x, const float *grad_y, float *grad_x, int64_t 
 int moma_enqueue(const float *keys, int64_t n, int64_t D, float *queue_f32, void *queue_bf16,
                  int64_t K, int64_t index, const int64_t *index_dev, int shard_rank,
                  int shard_world, int normalize, float eps, moma_stream_t stream);
+/* keys[i] is row key_start + i*key_stride of the step's key list: for a rank that only computed the
+ * keys it owns (K-sharded queue: every W-th row, see moma_attn_fwd_rows). */
+int moma_enqueue_strided(const float *keys, int64_t n, int64_t D, float *queue_f32, void *queue_bf16,
+                         int64_t K, int64_t index, const int64_t *index_dev, int shard_rank,
+                         int shard_world, int64_t key_start, int64_t key_stride, moma_stream_t stream);
 int moma_enqueue_ids(int64_t n, int64_t index, const int64_t *index_dev, int64_t K,
                      int64_t *out_ids, moma_stream_t stream);
 int moma_pointer_advance(int64_t *index_dev, int64_t n, int64_t K, moma_stream_t stream);
@@ -140,6 +145,17 @@ int moma_nce_combine(const float *part_m, const float *part_l, const float *part
 int moma_nce_merge(const float *part_m, const float *part_l, const float *part_mmax,
                    const float *part_O, int n_parts, int64_t B, int64_t D, float *out_m,
                    float *out_l, float *out_mmax, float *out_O, moma_stream_t stream);
+/* Packed variants for the cross-rank exchange: one record per row
+ *   [ O (D floats) | m | l | mmax | pad ]  = D + 4 floats (rows stay 16-byte aligned),
+ * written by moma_nce_merge_packed ([B, D+4]) and consumed by moma_nce_combine_packed
+ * ([n_parts, B, D+4], e.g. the all-to-all receive buffer) -- no repacking kernels in between. */
+int moma_nce_merge_packed(const float *part_m, const float *part_l, const float *part_mmax,
+                          const float *part_O, int n_parts, int64_t B, int64_t D, float *packed,
+                          moma_stream_t stream);
+int moma_nce_combine_packed(const float *packed, int n_parts, const float *q_f32,
+                            const float *kpos_f32, int64_t B, int64_t D, float inv_T, int round_bf16,
+                            float dq_scale, float *loss_rows, float *dq_unit, int32_t *pos_is_max,
+                            float *max_logit, float *loss_mean, float *acc_pct, moma_stream_t stream);
 /* Escape hatch / tests: materialise logits[B, K+1] = cat(q.k, q queue^T) / T
  * exactly as mem_moco.py:29-49 lays them out (row stride K+1). */
 int moma_nce_logits(const void *q, const void *kpos, const void *queue, int64_t B, int64_t D,
@@ -160,6 +176,12 @@ int moma_nce_logits_qk(const float *q, const float *kpos, int64_t B, int64_t D, 
 int moma_attn_fwd(const float *x, const float *w_qkv, const float *b_qkv, const float *w_proj,
                   const float *b_proj, int64_t N, int64_t C, int H, float *y, float *qkv,
                   float *o, float *lse, float *attn_probs, moma_stream_t stream);
+/* Forward for the query rows q_start + i*q_stride (i < q_count) only; keys / values from all N rows.
+ * y, o: [q_count, C]; lse: [H, q_count]; qkv: [N, 3C] scratch.  Forward only (no saved state). */
+int moma_attn_fwd_rows(const float *x, const float *w_qkv, const float *b_qkv, const float *w_proj,
+                       const float *b_proj, int64_t N, int64_t C, int H, int64_t q_start,
+                       int64_t q_stride, int64_t q_count, float *y, float *qkv, float *o, float *lse,
+                       moma_stream_t stream);
 size_t moma_attn_bwd_workspace_bytes(int64_t N, int64_t C, int H);
 /* Any of the gradient outputs may be NULL (skipped). Gradients are overwritten,
  * not accumulated. */

@@ -28,6 +28,7 @@ SIGNATURES = {
     "moma_l2norm_fwd": (c_int, [_vp, _vp, _i64, _i64, c_float, _vp]),
     "moma_l2norm_bwd": (c_int, [_vp, _vp, _vp, _i64, _i64, c_float, _vp]),
     "moma_enqueue": (c_int, [_vp, _i64, _i64, _vp, _vp, _i64, _i64, _vp, c_int, c_int, c_int, c_float, _vp]),
+    "moma_enqueue_strided": (c_int, [_vp, _i64, _i64, _vp, _vp, _i64, _i64, _vp, c_int, c_int, _i64, _i64, _vp]),
     "moma_enqueue_ids": (c_int, [_i64, _i64, _vp, _i64, _vp, _vp]),
     "moma_pointer_advance": (c_int, [_vp, _i64, _i64, _vp]),
     "moma_cast_bf16": (c_int, [_vp, _vp, _i64, _vp]),
@@ -36,12 +37,16 @@ SIGNATURES = {
     "moma_nce_combine": (c_int, [_vp, _vp, _vp, _vp, c_int, _vp, _vp, _i64, _i64, c_float, c_int, c_float,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "moma_nce_merge": (c_int, [_vp, _vp, _vp, _vp, c_int, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "moma_nce_merge_packed": (c_int, [_vp, _vp, _vp, _vp, c_int, _i64, _i64, _vp, _vp]),
+    "moma_nce_combine_packed": (c_int, [_vp, c_int, _vp, _vp, _i64, _i64, c_float, c_int, c_float,
+                                        _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "moma_nce_logits": (c_int, [_vp, _vp, _vp, _i64, _i64, _i64, c_float, c_int, _vp, _vp]),
     "moma_nce_logits_qk": (c_int, [_vp, _vp, _i64, _i64, c_float, _vp, _vp]),
     "moma_attn_fwd": (c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "moma_debug_nce_tc": (c_int, [_vp, _vp, _i64, _i64, _i64, c_float, c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "moma_debug_tc_error": (c_int, []),
     "moma_debug_launch_count": (ctypes.c_longlong, [c_int]),
+    "moma_attn_fwd_rows": (c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, c_int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "moma_attn_bwd_workspace_bytes": (c_size_t, [_i64, _i64, c_int]),
     "moma_attn_bwd": (c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, c_int,
                               _vp, _vp, _vp, _vp, _vp, _vp, c_size_t, _vp]),

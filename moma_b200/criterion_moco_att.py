@@ -128,6 +128,16 @@ class Attention(nn.Module):
                              self.num_heads)
 
 
+    def forward_rows(self, x, q_start, q_stride, q_count):
+        """Rows q_start + i * q_stride (i < q_count) of ``self(x)`` without computing the others; no autograd.
+        (K-sharded queue: a rank only enqueues every W-th attended key.)"""
+        if not self._fusable(x):
+            with torch.no_grad():
+                return self._composed(x)[q_start::q_stride][:q_count]
+        return ops.attention_rows(x, self.qkv.weight, self.qkv.bias, self.proj.weight, self.proj.bias,
+                                  self.num_heads, q_start, q_stride, q_count)
+
+
 class Attention_viz(Attention):
     """reference :171-197: also returns the attention map [1, H, N, N]."""
 

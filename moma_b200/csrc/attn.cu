@@ -222,7 +222,9 @@ __device__ __forceinline__ void acc_tile(const float* p_s, const float* v_s, int
 template <int HD, int RW>
 __global__ void __launch_bounds__(kAThreads)
 attn_fwd_kernel(const float* __restrict__ qkv, int N, int C, float scale, float* __restrict__ o,
-                float* __restrict__ lse) {
+                float* __restrict__ lse, int q_start, int q_stride, int NQ) {
+    // queries are the NQ rows q_start + i * q_stride of the N tokens (all rows by default); o / lse are
+    // indexed by the compact query index i
     using Cfg = AttnCfg<HD, RW>;
     constexpr int kAR = Cfg::AR;
     constexpr int KT = Cfg::KT_FWD, CC = KT / 32, LDP = KT + 4;
@@ -238,7 +240,15 @@ attn_fwd_kernel(const float* __restrict__ qkv, int N, int C, float scale, float*
     const float* kg = qkv + C + h * HD;
     const float* vg = qkv + 2 * C + h * HD;
 
-    load_rows<HD>(q_s, qg, ldg, i0, kAR, N);
+    {
+        constexpr int NV = HD / 4;
+        for (int i = threadIdx.x; i < kAR * NV; i += kAThreads) {
+            const int r = i / NV, v = i - r * NV;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i0 + r < NQ) a = *reinterpret_cast<const float4*>(qg + (int64_t)(q_start + (i0 + r) * q_stride) * ldg + 4 * v);
+            *reinterpret_cast<float4*>(q_s + r * Cfg::LD + 4 * v) = a;
+        }
+    }
     float m_run[RW], l_run[RW];
 #pragma unroll
     for (int r = 0; r < RW; ++r) { m_run[r] = -CUDART_INF_F; l_run[r] = 0.f; }
@@ -292,7 +302,7 @@ attn_fwd_kernel(const float* __restrict__ qkv, int N, int C, float scale, float*
 #pragma unroll
         for (int rr = 0; rr < RW; ++rr) lr = (rr == r + roff) ? l_run[rr] : lr;
         const int row = i0 + warp * RW + roff + r;
-        if (row < N) {
+        if (row < NQ) {
 #pragma unroll
             for (int c = 0; c < Cfg::CPL; ++c)
                 o[(int64_t)row * C + h * HD + cbase + 32 * c] = acc[r][c] / lr;
@@ -303,7 +313,7 @@ attn_fwd_kernel(const float* __restrict__ qkv, int N, int C, float scale, float*
 #pragma unroll
         for (int rr = 0; rr < RW; ++rr) { mr = (rr == lane) ? m_run[rr] : mr; lr = (rr == lane) ? l_run[rr] : lr; }
         const int row = i0 + warp * RW + lane;
-        if (row < N) lse[(int64_t)h * N + row] = mr + logf(lr);
+        if (row < NQ) lse[(int64_t)h * NQ + row] = mr + logf(lr);
     }
 }
 
@@ -480,11 +490,13 @@ template <int HD, int RW> static size_t dkv_smem() {
 }
 
 template <int HD, int RW>
-static void launch_fwd_rw(const float* qkv, int N, int C, int H, float scale, float* o, float* lse, cudaStream_t st) {
+static void launch_fwd_rw(const float* qkv, int N, int C, int H, float scale, float* o, float* lse, cudaStream_t st,
+                          int q_start, int q_stride, int NQ) {
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(attn_fwd_kernel<HD, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<HD, RW>()); attr = true; }
     constexpr int AR = 4 * RW;
-    attn_fwd_kernel<HD, RW><<<dim3((N + AR - 1) / AR, H), kAThreads, fwd_smem<HD, RW>(), st>>>(qkv, N, C, scale, o, lse);
+    attn_fwd_kernel<HD, RW><<<dim3((NQ + AR - 1) / AR, H), kAThreads, fwd_smem<HD, RW>(), st>>>(qkv, N, C, scale, o, lse,
+                                                                                             q_start, q_stride, NQ);
 }
 template <int HD, int RW>
 static void launch_bwd_rw(const float* qkv, const float* dO, const float* lse, const float* delta, int N, int C, int H,
@@ -510,12 +522,14 @@ template <int HD> static int pick_rw(int N, int H) {
     return rw_min;
 }
 template <int HD>
-static void launch_fwd(const float* qkv, int N, int C, int H, float scale, float* o, float* lse, cudaStream_t st) {
-    switch (pick_rw<HD>(N, H)) {
-        case 8: launch_fwd_rw<HD, 8>(qkv, N, C, H, scale, o, lse, st); break;
-        case 4: launch_fwd_rw<HD, 4>(qkv, N, C, H, scale, o, lse, st); break;
-        default: if constexpr (HD >= 16) launch_fwd_rw<HD, 2>(qkv, N, C, H, scale, o, lse, st);
-                 else launch_fwd_rw<HD, 4>(qkv, N, C, H, scale, o, lse, st);
+static void launch_fwd(const float* qkv, int N, int C, int H, float scale, float* o, float* lse, cudaStream_t st,
+                       int q_start = 0, int q_stride = 1, int NQ = -1) {
+    if (NQ < 0) NQ = N;
+    switch (pick_rw<HD>(NQ, H)) {
+        case 8: launch_fwd_rw<HD, 8>(qkv, N, C, H, scale, o, lse, st, q_start, q_stride, NQ); break;
+        case 4: launch_fwd_rw<HD, 4>(qkv, N, C, H, scale, o, lse, st, q_start, q_stride, NQ); break;
+        default: if constexpr (HD >= 16) launch_fwd_rw<HD, 2>(qkv, N, C, H, scale, o, lse, st, q_start, q_stride, NQ);
+                 else launch_fwd_rw<HD, 4>(qkv, N, C, H, scale, o, lse, st, q_start, q_stride, NQ);
     }
 }
 template <int HD>
@@ -569,6 +583,36 @@ extern "C" __attribute__((visibility("default"))) int moma_attn_fwd(const float*
     sgemm(o, C, 1, w_proj, C, 1, b_proj, y, C, n, c, c, st);
     MOMA_CUDA_LAUNCH_CHECK("attn_fwd");
     note_launches(attn_probs ? 4 : 3);
+    return MOMA_OK;
+}
+
+// Forward for a strided SUBSET of the query rows (rows q_start + i * q_stride, i < q_count): keys / values still
+// come from all N tokens.  Used by the K-sharded queue, where a rank only needs the attended keys it will
+// enqueue (every W-th row of the all-gathered keys): N * N / W score work instead of N * N.  No backward.
+extern "C" __attribute__((visibility("default"))) int moma_attn_fwd_rows(
+    const float* x, const float* w_qkv, const float* b_qkv, const float* w_proj, const float* b_proj, int64_t N,
+    int64_t C, int H, int64_t q_start, int64_t q_stride, int64_t q_count, float* y, float* qkv, float* o,
+    float* lse, moma_stream_t stream) {
+    int rc = check_attn("attn_fwd_rows", N, C, H);
+    if (rc != MOMA_OK) return rc;
+    MOMA_REQUIRE(x && w_qkv && w_proj && b_proj && y && qkv && o && lse, MOMA_ERR_INVALID, "attn_fwd_rows: null pointer");
+    MOMA_REQUIRE(q_count > 0 && q_stride > 0 && q_start >= 0 && q_start + (q_count - 1) * q_stride < N, MOMA_ERR_INVALID,
+                 "attn_fwd_rows: row subset out of range");
+    MOMA_REQUIRE(aligned16(qkv) && aligned16(o), MOMA_ERR_ALIGN, "attn_fwd_rows: qkv/o must be 16-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    const int n = (int)N, c = (int)C, hd = c / H, nq = (int)q_count;
+    const float scale = 1.0f / sqrtf((float)hd);
+    sgemm(x, C, 1, w_qkv, C, 1, b_qkv, qkv, 3 * C, n, 3 * c, c, st);
+    switch (hd) {
+        case 8: launch_fwd<8>(qkv, n, c, H, scale, o, lse, st, (int)q_start, (int)q_stride, nq); break;
+        case 16: launch_fwd<16>(qkv, n, c, H, scale, o, lse, st, (int)q_start, (int)q_stride, nq); break;
+        case 32: launch_fwd<32>(qkv, n, c, H, scale, o, lse, st, (int)q_start, (int)q_stride, nq); break;
+        case 64: launch_fwd<64>(qkv, n, c, H, scale, o, lse, st, (int)q_start, (int)q_stride, nq); break;
+        default: launch_fwd<128>(qkv, n, c, H, scale, o, lse, st, (int)q_start, (int)q_stride, nq); break;
+    }
+    sgemm(o, C, 1, w_proj, C, 1, b_proj, y, C, nq, c, c, st);
+    MOMA_CUDA_LAUNCH_CHECK("attn_fwd_rows");
+    note_launches(3);
     return MOMA_OK;
 }
 

@@ -73,12 +73,14 @@ __device__ __forceinline__ uint2 pack_bf16x4(const float4& a) {
 __global__ void __launch_bounds__(kEnqWarps * 32)
 enqueue_kernel(const float* __restrict__ keys, int64_t n, int64_t D, float* __restrict__ queue,
                __nv_bfloat16* __restrict__ shadow, int64_t K, int64_t index,
-               const int64_t* __restrict__ index_dev, int rank, int world, int normalize, float eps) {
+               const int64_t* __restrict__ index_dev, int rank, int world, int normalize, float eps,
+               int64_t key_start, int64_t key_stride) {
     const int lane = threadIdx.x & 31;
     const int64_t j = (int64_t)blockIdx.x * kEnqWarps + (threadIdx.x >> 5);
     if (j >= n) return;
     if (index_dev) index = *index_dev;
-    const int64_t gid = (j + index) % K;
+    // provided row j is row key_start + j * key_stride of the step's key list (identity by default)
+    const int64_t gid = (key_start + j * key_stride + index) % K;
     if (gid % world != rank) return;
     const int64_t slot = gid / world;
     const float4* s4 = reinterpret_cast<const float4*>(keys + j * D);
@@ -163,19 +165,19 @@ extern "C" __attribute__((visibility("default"))) int moma_l2norm_bwd(const floa
     return MOMA_OK;
 }
 
-extern "C" __attribute__((visibility("default"))) int moma_enqueue(const float* keys, int64_t n, int64_t D, float* queue_f32,
-                            void* queue_bf16, int64_t K, int64_t index, const int64_t* index_dev,
-                            int shard_rank, int shard_world, int normalize, float eps,
-                            moma_stream_t stream) {
+static int enqueue_impl(const float* keys, int64_t n, int64_t D, float* queue_f32,
+                        void* queue_bf16, int64_t K, int64_t index, const int64_t* index_dev,
+                        int shard_rank, int shard_world, int normalize, float eps, int64_t key_start,
+                        int64_t key_stride, moma_stream_t stream) {
     int rc = check_rows("enqueue", keys, queue_f32, n, D);
     if (rc != MOMA_OK) return rc;
     MOMA_REQUIRE(K > 0 && shard_world >= 1 && shard_rank >= 0 && shard_rank < shard_world,
                  MOMA_ERR_INVALID, "enqueue: bad K/shard (%lld, %d/%d)", (long long)K, shard_rank, shard_world);
     MOMA_REQUIRE(K % shard_world == 0, MOMA_ERR_INVALID, "enqueue: K=%lld not divisible by shard_world=%d",
                  (long long)K, shard_world);
-    MOMA_REQUIRE(n <= K, MOMA_ERR_INVALID,
+    MOMA_REQUIRE(key_start >= 0 && key_stride >= 1 && key_start + (n > 0 ? n - 1 : 0) * key_stride < K, MOMA_ERR_INVALID,
                  "enqueue: n=%lld > K=%lld gives duplicate ids (undefined in the reference)",
-                 (long long)n, (long long)K);
+                 (long long)(key_start + n * key_stride), (long long)K);
     MOMA_REQUIRE(index_dev || (index >= 0 && index < K), MOMA_ERR_INVALID, "enqueue: index out of range");
     MOMA_REQUIRE(!queue_bf16 || (D % 8 == 0 && aligned16(queue_bf16)), MOMA_ERR_ALIGN,
                  "enqueue: bf16 shadow needs D %% 8 == 0 and 16-byte alignment");
@@ -183,10 +185,27 @@ extern "C" __attribute__((visibility("default"))) int moma_enqueue(const float* 
     const unsigned grid = (unsigned)((n + kEnqWarps - 1) / kEnqWarps);
     enqueue_kernel<<<grid, kEnqWarps * 32, 0, as_stream(stream)>>>(
         keys, n, D, queue_f32, static_cast<__nv_bfloat16*>(queue_bf16), K, index, index_dev,
-        shard_rank, shard_world, normalize, eps);
+        shard_rank, shard_world, normalize, eps, key_start, key_stride);
     MOMA_CUDA_LAUNCH_CHECK("enqueue");
     note_launches(1);
     return MOMA_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int moma_enqueue(const float* keys, int64_t n, int64_t D, float* queue_f32,
+                            void* queue_bf16, int64_t K, int64_t index, const int64_t* index_dev,
+                            int shard_rank, int shard_world, int normalize, float eps,
+                            moma_stream_t stream) {
+    return enqueue_impl(keys, n, D, queue_f32, queue_bf16, K, index, index_dev, shard_rank, shard_world, normalize,
+                        eps, 0, 1, stream);
+}
+
+// keys[i] is row key_start + i * key_stride of the step's key list (a rank that only computed the rows it owns)
+extern "C" __attribute__((visibility("default"))) int moma_enqueue_strided(const float* keys, int64_t n, int64_t D,
+                            float* queue_f32, void* queue_bf16, int64_t K, int64_t index, const int64_t* index_dev,
+                            int shard_rank, int shard_world, int64_t key_start, int64_t key_stride,
+                            moma_stream_t stream) {
+    return enqueue_impl(keys, n, D, queue_f32, queue_bf16, K, index, index_dev, shard_rank, shard_world, 0, 1e-12f,
+                        key_start, key_stride, stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int moma_enqueue_ids(int64_t n, int64_t index, const int64_t* index_dev, int64_t K,

@@ -202,6 +202,10 @@ nce_reduce_kernel(const float* __restrict__ part_m, const float* __restrict__ pa
                   const float* __restrict__ part_mmax, const float* __restrict__ part_O, int n_parts,
                   const float* __restrict__ q, const float* __restrict__ kpos, int B, int D, float inv_T,
                   int round_bf16, float dq_scale,
+                  int64_t st_ss /* stats stride between parts */, int64_t st_rs /* ... between rows */,
+                  int64_t o_ss /* O stride between parts */, int64_t o_rs /* ... between rows */,
+                  int64_t out_rs /* merged-partial output: row stride of the stats (1 = separate arrays) */,
+                  int64_t out_o_rs /* row stride of the O output */,
                   float* __restrict__ out_a /* loss_rows | out_m */, float* __restrict__ out_O /* dq | out_O */,
                   int32_t* __restrict__ pos_is_max, float* __restrict__ out_b /* max_logit | out_l */,
                   float* __restrict__ out_c /* - | out_mmax */) {
@@ -224,8 +228,8 @@ nce_reduce_kernel(const float* __restrict__ part_m, const float* __restrict__ pa
     }
     float mref = -CUDART_INF_F, mtrue = -CUDART_INF_F;
     for (int s = tid; s < n_parts; s += kCombThreads) {
-        mref = fmaxf(mref, part_m[(int64_t)s * B + row]);
-        mtrue = fmaxf(mtrue, part_mmax[(int64_t)s * B + row]);
+        mref = fmaxf(mref, part_m[(int64_t)s * st_ss + row * st_rs]);
+        mtrue = fmaxf(mtrue, part_mmax[(int64_t)s * st_ss + row * st_rs]);
     }
     mref = block_max(mref, red);
     mtrue = block_max(mtrue, red);
@@ -233,7 +237,7 @@ nce_reduce_kernel(const float* __restrict__ part_m, const float* __restrict__ pa
     const float wpos = kFinal ? expf(pos - mstar) : 0.f;
 
     float l_part = 0.f, l_tot = 0.f;
-    const int64_t sstride = (int64_t)B * D;
+    const int64_t sstride = o_ss;
     for (int d0 = 0; d0 < D; d0 += kCombMaxD) {
         float4 o[4];
 #pragma unroll
@@ -242,14 +246,14 @@ nce_reduce_kernel(const float* __restrict__ part_m, const float* __restrict__ pa
             const int cnt = min(kCombChunk, n_parts - s0);
             __syncthreads();
             for (int s = tid; s < cnt; s += kCombThreads) {
-                const int64_t base = (int64_t)(s0 + s) * B + row;
+                const int64_t base = (int64_t)(s0 + s) * st_ss + row * st_rs;
                 const float ms = part_m[base];
                 const float w = (ms == -CUDART_INF_F) ? 0.f : expf(ms - mstar);
                 s_w[s] = w;
                 if (d0 == 0) l_part += w * part_l[base];
             }
             __syncthreads();
-            const float* Op = part_O + ((int64_t)s0 * B + row) * D + d0;
+            const float* Op = part_O + (int64_t)s0 * o_ss + row * o_rs + d0;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int d = 4 * lane + 128 * c;              // column of this lane's float4
@@ -291,9 +295,9 @@ nce_reduce_kernel(const float* __restrict__ part_m, const float* __restrict__ pa
             const float ov = (s_o[0][d] + s_o[1][d]) + (s_o[2][d] + s_o[3][d]);
             if (kFinal) {
                 const float kv = round_bf16 ? bf16_round(kr[d0 + d]) : kr[d0 + d];
-                out_O[(int64_t)row * D + d0 + d] = ((ov + wpos * kv) / l_tot - kv) * inv_T * dq_scale;
+                out_O[(int64_t)row * out_o_rs + d0 + d] = ((ov + wpos * kv) / l_tot - kv) * inv_T * dq_scale;
             } else {
-                out_O[(int64_t)row * D + d0 + d] = ov;
+                out_O[(int64_t)row * out_o_rs + d0 + d] = ov;
             }
         }
     }
@@ -303,7 +307,7 @@ nce_reduce_kernel(const float* __restrict__ part_m, const float* __restrict__ pa
             pos_is_max[row] = (pos >= mtrue) ? 1 : 0;
             if (out_b) out_b[row] = fmaxf(pos, mtrue);
         } else {
-            out_a[row] = mref; out_b[row] = l_tot; out_c[row] = mtrue;
+            out_a[row * out_rs] = mref; out_b[row * out_rs] = l_tot; out_c[row * out_rs] = mtrue;
         }
     }
 }
@@ -464,7 +468,7 @@ extern "C" __attribute__((visibility("default"))) int moma_nce_combine(const flo
     MOMA_REQUIRE(D % 4 == 0 && aligned16(part_O), MOMA_ERR_ALIGN, "nce_combine: D %% 4 != 0 or part_O unaligned");
     nce_reduce_kernel<true><<<(unsigned)B, kCombThreads, 0, as_stream(stream)>>>(
         part_m, part_l, part_mmax, part_O, n_parts, q_f32, kpos_f32, (int)B, (int)D, inv_T, round_bf16, dq_scale,
-        loss_rows, dq_unit, pos_is_max, max_logit, nullptr);
+        B, 1, B * D, D, 1, D, loss_rows, dq_unit, pos_is_max, max_logit, nullptr);
     MOMA_CUDA_LAUNCH_CHECK("nce_combine");
     note_launches(1);
     if (loss_mean && acc_pct) {
@@ -483,10 +487,49 @@ extern "C" __attribute__((visibility("default"))) int moma_nce_merge(
                  MOMA_ERR_INVALID, "nce_merge: null pointer");
     MOMA_REQUIRE(D % 4 == 0 && aligned16(part_O), MOMA_ERR_ALIGN, "nce_merge: D %% 4 != 0 or part_O unaligned");
     nce_reduce_kernel<false><<<(unsigned)B, kCombThreads, 0, as_stream(stream)>>>(
-        part_m, part_l, part_mmax, part_O, n_parts, nullptr, nullptr, (int)B, (int)D, 1.f, 0, 1.f, out_m, out_O,
-        nullptr, out_l, out_mmax);
+        part_m, part_l, part_mmax, part_O, n_parts, nullptr, nullptr, (int)B, (int)D, 1.f, 0, 1.f,
+        B, 1, B * D, D, 1, D, out_m, out_O, nullptr, out_l, out_mmax);
     MOMA_CUDA_LAUNCH_CHECK("nce_merge");
     note_launches(1);
+    return MOMA_OK;
+}
+
+// Packed partial record per row: [O (D floats) | m | l | mmax | pad] = D + 4 floats (16-byte aligned rows),
+// the unit that travels between ranks for the K-sharded queue.
+extern "C" __attribute__((visibility("default"))) int moma_nce_merge_packed(
+    const float* part_m, const float* part_l, const float* part_mmax, const float* part_O, int n_parts,
+    int64_t B, int64_t D, float* packed, moma_stream_t stream) {
+    MOMA_REQUIRE(B > 0 && D > 0 && n_parts > 0, MOMA_ERR_INVALID, "nce_merge_packed: bad shape");
+    MOMA_REQUIRE(part_m && part_l && part_mmax && part_O && packed, MOMA_ERR_INVALID, "nce_merge_packed: null pointer");
+    MOMA_REQUIRE(D % 4 == 0 && aligned16(part_O) && aligned16(packed), MOMA_ERR_ALIGN, "nce_merge_packed: alignment");
+    const int64_t P = D + 4;
+    nce_reduce_kernel<false><<<(unsigned)B, kCombThreads, 0, as_stream(stream)>>>(
+        part_m, part_l, part_mmax, part_O, n_parts, nullptr, nullptr, (int)B, (int)D, 1.f, 0, 1.f,
+        B, 1, B * D, D, P, P, packed + D, packed, nullptr, packed + D + 1, packed + D + 2);
+    MOMA_CUDA_LAUNCH_CHECK("nce_merge_packed");
+    note_launches(1);
+    return MOMA_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int moma_nce_combine_packed(
+    const float* packed, int n_parts, const float* q_f32, const float* kpos_f32, int64_t B, int64_t D,
+    float inv_T, int round_bf16, float dq_scale, float* loss_rows, float* dq_unit, int32_t* pos_is_max,
+    float* max_logit, float* loss_mean, float* acc_pct, moma_stream_t stream) {
+    MOMA_REQUIRE(B > 0 && D > 0 && n_parts > 0, MOMA_ERR_INVALID, "nce_combine_packed: bad shape");
+    MOMA_REQUIRE(packed && q_f32 && kpos_f32 && loss_rows && dq_unit && pos_is_max, MOMA_ERR_INVALID,
+                 "nce_combine_packed: null pointer");
+    MOMA_REQUIRE(D % 4 == 0 && aligned16(packed), MOMA_ERR_ALIGN, "nce_combine_packed: alignment");
+    const int64_t P = D + 4;
+    nce_reduce_kernel<true><<<(unsigned)B, kCombThreads, 0, as_stream(stream)>>>(
+        packed + D, packed + D + 1, packed + D + 2, packed, n_parts, q_f32, kpos_f32, (int)B, (int)D, inv_T,
+        round_bf16, dq_scale, B * P, P, B * P, P, 1, D, loss_rows, dq_unit, pos_is_max, max_logit, nullptr);
+    MOMA_CUDA_LAUNCH_CHECK("nce_combine_packed");
+    note_launches(1);
+    if (loss_mean && acc_pct) {
+        nce_finalize_kernel<<<1, 256, 0, as_stream(stream)>>>(loss_rows, pos_is_max, (int)B, loss_mean, acc_pct);
+        MOMA_CUDA_LAUNCH_CHECK("nce_finalize");
+        note_launches(1);
+    }
     return MOMA_OK;
 }
 

@@ -145,10 +145,16 @@ def cast_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
 
 def enqueue(keys: torch.Tensor, queue: torch.Tensor, shadow: Optional[torch.Tensor], K: int, index: int,
             rank: int = 0, world: int = 1, normalize: bool = False, eps: float = 1e-12,
-            index_dev: Optional[torch.Tensor] = None) -> None:
-    """queue[(index + j) % K] = keys[j]  (mem_moco.py:17-27), cyclically sharded when world > 1."""
+            index_dev: Optional[torch.Tensor] = None, key_start: int = 0, key_stride: int = 1) -> None:
+    """queue[(index + j) % K] = keys[j]  (mem_moco.py:17-27), cyclically sharded when world > 1.
+    With key_start / key_stride, keys[i] stands for row key_start + i * key_stride of the step's key list."""
     _need_cuda(keys, queue, shadow)
     keys = _f32c(keys.detach())
+    if key_start != 0 or key_stride != 1:
+        check(_lib.load().moma_enqueue_strided(_p(keys), keys.shape[0], keys.shape[1], _p(queue), _p(shadow), K,
+                                               int(index), _p(index_dev), rank, world, int(key_start),
+                                               int(key_stride), _stream()))
+        return
     check(_lib.load().moma_enqueue(_p(keys), keys.shape[0], keys.shape[1], _p(queue), _p(shadow), K, int(index),
                                    _p(index_dev), rank, world, int(normalize), eps, _stream()))
 
@@ -215,6 +221,34 @@ def nce_merge(stats: torch.Tensor, O: torch.Tensor):
     check(_lib.load().moma_nce_merge(_p(stats[0]), _p(stats[1]), _p(stats[2]), _p(O), n_parts, B, D,
                                      _p(out_s[0]), _p(out_s[1]), _p(out_s[2]), _p(out_O), _stream()))
     return out_s, out_O
+
+
+def nce_merge_packed(stats: torch.Tensor, O: torch.Tensor) -> torch.Tensor:
+    """Fold split partials into one packed record per row: [B, D + 4] = (O | m | l | mmax | pad)."""
+    n_parts, B = stats.shape[1], stats.shape[2]
+    D = O.shape[2]
+    packed = torch.empty((B, D + 4), dtype=torch.float32, device=O.device)
+    check(_lib.load().moma_nce_merge_packed(_p(stats[0]), _p(stats[1]), _p(stats[2]), _p(O), n_parts, B, D,
+                                            _p(packed), _stream()))
+    return packed
+
+
+def nce_combine_packed(packed: torch.Tensor, q_f32: torch.Tensor, k_f32: torch.Tensor, inv_T: float,
+                       round_bf16: bool, dq_scale: float):
+    """Combine packed records [n_parts, B, D + 4] (+ positive column) ->
+    (rows, dq, pos_is_max, max_logit, loss_mean, acc_pct)."""
+    n_parts, B, P = packed.shape
+    D = P - 4
+    dev = q_f32.device
+    rows = torch.empty(B, dtype=torch.float32, device=dev)
+    dq = torch.empty((B, D), dtype=torch.float32, device=dev)
+    pim = torch.empty(B, dtype=torch.int32, device=dev)
+    mx = torch.empty(B, dtype=torch.float32, device=dev)
+    fin = torch.empty(2, dtype=torch.float32, device=dev)
+    check(_lib.load().moma_nce_combine_packed(_p(packed), n_parts, _p(q_f32), _p(k_f32), B, D, inv_T,
+                                              int(round_bf16), float(dq_scale), _p(rows), _p(dq), _p(pim), _p(mx),
+                                              _p(fin), fin.data_ptr() + 4, _stream()))
+    return rows, dq, pim, mx, fin[0], fin[1:2]
 
 
 def nce_operands(q: torch.Tensor, k: torch.Tensor, precision: str):
@@ -388,6 +422,25 @@ def attention(x, w_qkv, b_qkv, w_proj, b_proj, num_heads: int, want_probs: bool 
     if x.dim() != 2:
         raise RuntimeError("moma_b200.attention: expects [N, C]")
     return _Attention.apply(x, w_qkv, b_qkv, w_proj, b_proj, int(num_heads), bool(want_probs))
+
+
+def attention_rows(x, w_qkv, b_qkv, w_proj, b_proj, num_heads: int, q_start: int, q_stride: int, q_count: int):
+    """Attention output for the query rows q_start + i * q_stride only (keys / values from all rows of x).
+    Forward only: used for the keys a rank of the K-sharded queue will enqueue."""
+    _need_cuda(x, w_qkv, w_proj)
+    with torch.no_grad():
+        xc, wq, wp, bp = _f32c(x), _f32c(w_qkv), _f32c(w_proj), _f32c(b_proj)
+        bq = _f32c(b_qkv) if b_qkv is not None else None
+        N, C = xc.shape
+        dev = xc.device
+        y = torch.empty((q_count, C), dtype=torch.float32, device=dev)
+        qkv = torch.empty((N, 3 * C), dtype=torch.float32, device=dev)
+        o = torch.empty((q_count, C), dtype=torch.float32, device=dev)
+        lse = torch.empty((num_heads, q_count), dtype=torch.float32, device=dev)
+        check(_lib.load().moma_attn_fwd_rows(_p(xc), _p(wq), _p(bq), _p(wp), _p(bp), N, C, int(num_heads),
+                                             int(q_start), int(q_stride), int(q_count), _p(y), _p(qkv), _p(o),
+                                             _p(lse), _stream()))
+    return y
 
 
 def attention_supported(C: int, H: int) -> bool:

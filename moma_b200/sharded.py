@@ -98,7 +98,7 @@ class ShardedMoCo(BaseMoCo):
 
     # ---- exchange of the per-rank partials ------------------------------------------------------
     def _exchange(self, packed: torch.Tensor) -> torch.Tensor:
-        """packed [W(dst), B_local, D + 3] -> [W(src), B_local, D + 3] for this rank's queries."""
+        """packed [W(dst), B_local, D + 4] -> [W(src), B_local, D + 4] for this rank's queries."""
         backend = dist.get_backend(self.group)
         out = torch.empty_like(packed)
         if backend == "nccl":
@@ -106,7 +106,18 @@ class ShardedMoCo(BaseMoCo):
             return out
         return self._all_gather(packed)[:, self.rank].contiguous()
 
-    def forward(self, q, k, all_k=None):
+    def owned_rows(self, n: int):
+        """(start, stride, count) of the rows of this step's n all-gathered keys that this rank will
+        enqueue: global id (index + j) % K is owned iff (index + j) % W == rank.  Constant across steps
+        when n % W == 0 (the pointer advances by n)."""
+        W = self.world
+        if n % W != 0:
+            raise ValueError("owned_rows needs n % world == 0")
+        return (self.rank - self.index) % W, W, n // W
+
+    def forward(self, q, k, all_k=None, owned_k=None):
+        """As MoCo.forward.  ``owned_k`` (optional, instead of ``all_k``): only the rows
+        ``owned_rows(n)`` of the step's keys, e.g. from ``Attention.forward_rows``."""
         bsz, D = q.shape
         W = self.world
         k = k.detach()
@@ -127,26 +138,30 @@ class ShardedMoCo(BaseMoCo):
             # 2. local pass over this rank's K / W rows for all n queries, then fold the splits
             queue = shadow if use_bf16 else memory_shard
             stats, Opart = ops.nce_partial(all_q, queue, inv_T, dtype)
-            stats, Opart = ops.nce_merge(stats, Opart)                  # [3, 1, n], [1, n, D]
-            # 3. exchange: pack (O | m | l | mmax) per row, route rows to their owner rank
-            packed = torch.cat([Opart[0], stats[:, 0].t()], dim=1).view(W, bsz, D + 3)
-            recv = self._exchange(packed)                               # [W(src), bsz, D + 3]
-            O_all = recv[:, :, :D].contiguous()
-            st_all = recv[:, :, D:].permute(2, 0, 1).contiguous()       # [3, W, bsz]
-            # 4. combine with the positive column
-            rows, dq, pim, mx, loss, acc = ops.nce_combine(st_all, O_all, q32, k32, inv_T, rnd, 1.0 / bsz,
-                                                           want_mean=True)
+            packed = ops.nce_merge_packed(stats, Opart)                 # [n, D + 4] = (O | m | l | mmax | pad)
+            # 3. exchange: rows are ordered by owner rank, so the records route with one all-to-all
+            recv = self._exchange(packed.view(W, bsz, D + 4))           # [W(src), bsz, D + 4]
+            # 4. combine with the positive column (reads the receive buffer in place)
+            rows, dq, pim, mx, loss, acc = ops.nce_combine_packed(recv, q32, k32, inv_T, rnd, 1.0 / bsz)
             return loss, rows, pim, mx, acc, dq
 
         nce = ops.nce_fused(q, k, compute)
         shape = (bsz, self.K + 1) if bsz != 1 else (self.K + 1,)
         logits = LazyLogits(shape, q.device, nce, labels, _stale_after_enqueue)
         # 5. enqueue the rows this rank owns
-        all_k = all_k if all_k is not None else k
         with torch.no_grad():
-            if all_k.shape[0] > self.K:
-                raise RuntimeError("enqueue of more rows than K (duplicate ids)")
-            ops.enqueue(all_k, self.memory_shard, shadow if use_bf16 else self._shadow_of(self.memory_shard, create=False),
-                        self.K, self.index, rank=self.rank, world=W, index_dev=self._index_dev)
-        self._update_pointer(all_k.size(0))
+            sh = shadow if use_bf16 else self._shadow_of(self.memory_shard, create=False)
+            if owned_k is not None:
+                n = owned_k.shape[0] * W
+                start, stride, count = self.owned_rows(n)
+                ops.enqueue(owned_k, self.memory_shard, sh, self.K, self.index, rank=self.rank, world=W,
+                            index_dev=self._index_dev, key_start=start, key_stride=stride)
+            else:
+                all_k = all_k if all_k is not None else k
+                n = all_k.shape[0]
+                if n > self.K:
+                    raise RuntimeError("enqueue of more rows than K (duplicate ids)")
+                ops.enqueue(all_k, self.memory_shard, sh, self.K, self.index, rank=self.rank, world=W,
+                            index_dev=self._index_dev)
+        self._update_pointer(n)
         return logits, labels

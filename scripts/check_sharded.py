@@ -42,7 +42,11 @@ def main():
                 k = torch.randn(B, D, device="cuda") * 0.6
                 all_k = ContrastTrainer._global_gather(k)
                 lr, labr = rep(q1, k, all_k)
-                ls, labs = sh(q2, k, all_k)
+                if step == 1:       # only the rows this rank owns (what Attention.forward_rows would deliver)
+                    start, stride, count = sh.owned_rows(all_k.shape[0])
+                    ls, labs = sh(q2, k, owned_k=all_k[start::stride][:count].contiguous())
+                else:
+                    ls, labs = sh(q2, k, all_k)
                 loss_r, loss_s = ce(lr, labr), ce(ls, labs)
                 loss_r.backward(); loss_s.backward()
                 e_loss = abs(loss_r.item() - loss_s.item()) / abs(loss_r.item())

@@ -499,3 +499,55 @@ def test_graphed_step_matches_eager(ops):
             assert torch.allclose(fs_g.grad, want[1], rtol=1e-5, atol=1e-8)
             assert torch.equal(c_g.memory, want[2]) and c_g.index == want[3]
         assert c_g.index == (8 * 48) % 160                                   # wrapped twice
+
+
+def test_packed_merge_and_combine(ops):
+    """The packed partial records used for the cross-rank exchange give the same result as the
+    unpacked path, and emulated shards (cyclic split of the queue) merge to the replicated answer."""
+    from moma_b200._lib import F32
+    rng = np.random.default_rng(11)
+    B, D, K, T, W = 96, 64, 1024, 0.15, 4
+    q = (rng.standard_normal((B, D)) * 0.7).astype(np.float32)
+    k = (rng.standard_normal((B, D)) * 0.7).astype(np.float32)
+    queue = O.normalize(rng.standard_normal((K, D))).astype(np.float32)
+    loss_o, rows_o, dq_o, pim_o = O.nce_loss_and_grad(q.astype(np.float64), k.astype(np.float64), queue.astype(np.float64), T)
+    qt, kt = cu(q), cu(k)
+    recs = []
+    for r in range(W):                                   # rank r owns rows r, r + W, ...
+        shard = cu(queue[r::W].copy())
+        stats, Op = ops.nce_partial(qt, shard, 1 / T, F32, 3)
+        packed = ops.nce_merge_packed(stats, Op)
+        assert tuple(packed.shape) == (B, D + 4)
+        s1, O1 = ops.nce_merge(stats, Op)
+        assert torch.allclose(packed[:, :D], O1[0], rtol=1e-6, atol=1e-7)
+        assert torch.allclose(packed[:, D:D + 3].t(), s1[:, 0], rtol=1e-6, atol=1e-7)
+        recs.append(packed)
+    rows, dq, pim, mx, loss, acc = ops.nce_combine_packed(torch.stack(recs), qt, kt, 1 / T, False, 1.0 / B)
+    assert rel(npy(rows), rows_o) < TOL and rel(npy(dq), dq_o) < TOL
+    assert abs(loss.item() - loss_o) < TOL * abs(loss_o)
+    assert acc.item() == pytest.approx(pim_o.mean() * 100) and np.array_equal(pim.cpu().numpy().astype(bool), pim_o)
+
+
+def test_attention_row_subset_and_strided_enqueue(ops):
+    """forward_rows == the same rows of the full attention; strided enqueue == enqueue of the full list."""
+    from moma_b200 import Attention
+    torch.manual_seed(1)
+    att = Attention(128, num_heads=4, qkv_bias=True).cuda()
+    x = torch.randn(200, 128, device="cuda")
+    with torch.no_grad():
+        full = att(x)
+    for start, stride in ((0, 1), (3, 4), (1, 8), (7, 8)):
+        count = (200 - start + stride - 1) // stride
+        sub = att.forward_rows(x, start, stride, count)
+        assert torch.allclose(sub, full[start::stride], rtol=1e-5, atol=1e-6), (start, stride)
+    rng = np.random.default_rng(5)
+    K, D, n, W = 64, 32, 16, 4
+    full_q = rng.standard_normal((K, D)).astype(np.float32)
+    keys = rng.standard_normal((n, D)).astype(np.float32)
+    for rank in range(W):
+        index = 58                                    # wraps
+        want = full_q.copy(); O.update_memory(want, keys, index)
+        shard = cu(full_q[rank::W].copy())
+        start = (rank - index) % W
+        ops.enqueue(cu(keys[start::W].copy()), shard, None, K, index, rank=rank, world=W, key_start=start, key_stride=W)
+        assert np.array_equal(npy(shard), want[rank::W])

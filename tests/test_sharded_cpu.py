@@ -31,23 +31,25 @@ def _install_oracle_backend():
                           np.stack([p[0] for p in parts])])
         return torch.from_numpy(stats).float(), torch.from_numpy(np.stack([p[2] for p in parts])).float()
 
-    def nce_merge(stats, Op):
+    def nce_merge_packed(stats, Op):
         m, l, mm, O_ = stats[0].double(), stats[1].double(), stats[2].double(), Op.double()
         mref = m.max(0).values
         w = torch.exp(m - mref)
-        out_s = torch.stack([mref, (w * l).sum(0), mm.max(0).values]).unsqueeze(1).float()
-        return out_s, (w.unsqueeze(-1) * O_).sum(0, keepdim=True).float()
+        Om = (w.unsqueeze(-1) * O_).sum(0)
+        B = Om.shape[0]
+        return torch.cat([Om, mref[:, None], (w * l).sum(0)[:, None], mm.max(0).values[:, None],
+                          torch.zeros(B, 1, dtype=torch.float64)], dim=1).float()
 
-    def nce_combine(stats, Op, q32, k32, inv_T, round_bf16=False, dq_scale=1.0, want_mean=False):
-        parts = [(stats[0, s].double().numpy(), stats[1, s].double().numpy(), Op[s].double().numpy())
-                 for s in range(stats.shape[1])]
+    def nce_combine_packed(packed, q32, k32, inv_T, round_bf16, dq_scale):
+        D = packed.shape[2] - 4
+        parts = [(packed[s, :, D].double().numpy(), packed[s, :, D + 1].double().numpy(),
+                  packed[s, :, :D].double().numpy()) for s in range(packed.shape[0])]
         rows, dq, pim = O.nce_merge(parts, q32.double().numpy(), k32.double().numpy(), 1.0 / inv_T)
-        mx = np.maximum(stats[2].double().numpy().max(0), (q32.double().numpy() * k32.double().numpy()).sum(1) * inv_T)
-        out = (torch.from_numpy(rows).float(), torch.from_numpy(dq * dq_scale).float(),
-               torch.from_numpy(pim.astype(np.int32)), torch.from_numpy(mx).float())
-        if want_mean:
-            out += (torch.tensor(rows.mean(), dtype=torch.float32), torch.tensor([pim.mean() * 100.0], dtype=torch.float32))
-        return out
+        mx = np.maximum(packed[:, :, D + 2].double().numpy().max(0),
+                        (q32.double().numpy() * k32.double().numpy()).sum(1) * inv_T)
+        return (torch.from_numpy(rows).float(), torch.from_numpy(dq * dq_scale).float(),
+                torch.from_numpy(pim.astype(np.int32)), torch.from_numpy(mx).float(),
+                torch.tensor(rows.mean(), dtype=torch.float32), torch.tensor([pim.mean() * 100.0], dtype=torch.float32))
 
     def enqueue(keys, queue, shadow, K, index, rank=0, world=1, normalize=False, eps=1e-12, index_dev=None):
         ids = O.enqueue_ids(keys.shape[0], index, K)
@@ -56,7 +58,8 @@ def _install_oracle_backend():
             if owner[j] == rank:
                 queue[int(slot[j])] = keys[j].detach()
 
-    ops.nce_partial, ops.nce_merge, ops.nce_combine, ops.enqueue = nce_partial, nce_merge, nce_combine, enqueue
+    ops.nce_partial, ops.enqueue = nce_partial, enqueue
+    ops.nce_merge_packed, ops.nce_combine_packed = nce_merge_packed, nce_combine_packed
     ops.bf16_supported = lambda D: False
     ops.set_precision("fp32")
 
