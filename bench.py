@@ -278,7 +278,8 @@ def run_ours(args, cfg, rank, world, local_rank):
     from moma_b200.graphed import GraphedStep
     rows_per_step = B * world
     lib.moma_debug_launch_count(1)
-    graphed = GraphedStep(cs.step_overlapped, contrast=cs.contrast, rows_per_step=rows_per_step, warmup=3)
+    step_fn = cs.step if os.environ.get("MOMA_BENCH_SEQ") else cs.step_overlapped
+    graphed = GraphedStep(step_fn, contrast=cs.contrast, rows_per_step=rows_per_step, warmup=3)
     launches_per_step = int(lib.moma_debug_launch_count(1)) // 4       # 3 warm-up calls + 1 captured call
     for _ in range(3):
         graphed.replay()

@@ -500,7 +500,7 @@ static void launch_fwd_rw(const float* qkv, int N, int C, int H, float scale, fl
 }
 template <int HD, int RW>
 static void launch_bwd_rw(const float* qkv, const float* dO, const float* lse, const float* delta, int N, int C, int H,
-                          float scale, float* dqkv, cudaStream_t st) {
+                          float scale, float* dqkv, cudaStream_t st, cudaStream_t st2) {
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(attn_bwd_dq_kernel<HD, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dq_smem<HD, RW>());
@@ -509,8 +509,9 @@ static void launch_bwd_rw(const float* qkv, const float* dO, const float* lse, c
     }
     constexpr int AR = 4 * RW;
     const dim3 grid((N + AR - 1) / AR, H);
+    // dQ and dK/dV are independent: two streams (st2 was forked from st by the caller)
     attn_bwd_dq_kernel<HD, RW><<<grid, kAThreads, dq_smem<HD, RW>(), st>>>(qkv, dO, lse, delta, N, C, scale, dqkv);
-    attn_bwd_dkv_kernel<HD, RW><<<grid, kAThreads, dkv_smem<HD, RW>(), st>>>(qkv, dO, lse, delta, N, C, scale, dqkv);
+    attn_bwd_dkv_kernel<HD, RW><<<grid, kAThreads, dkv_smem<HD, RW>(), st2>>>(qkv, dO, lse, delta, N, C, scale, dqkv);
 }
 
 // rows per warp: the largest of {8, 4, 2} (but RW * HD >= 32) that still gives about one CTA per SM
@@ -534,13 +535,34 @@ static void launch_fwd(const float* qkv, int N, int C, int H, float scale, float
 }
 template <int HD>
 static void launch_bwd(const float* qkv, const float* dO, const float* lse, const float* delta, int N, int C, int H,
-                       float scale, float* dqkv, cudaStream_t st) {
+                       float scale, float* dqkv, cudaStream_t st, cudaStream_t st2) {
     switch (pick_rw<HD>(N, H)) {
-        case 8: launch_bwd_rw<HD, 8>(qkv, dO, lse, delta, N, C, H, scale, dqkv, st); break;
-        case 4: launch_bwd_rw<HD, 4>(qkv, dO, lse, delta, N, C, H, scale, dqkv, st); break;
-        default: if constexpr (HD >= 16) launch_bwd_rw<HD, 2>(qkv, dO, lse, delta, N, C, H, scale, dqkv, st);
-                 else launch_bwd_rw<HD, 4>(qkv, dO, lse, delta, N, C, H, scale, dqkv, st);
+        case 8: launch_bwd_rw<HD, 8>(qkv, dO, lse, delta, N, C, H, scale, dqkv, st, st2); break;
+        case 4: launch_bwd_rw<HD, 4>(qkv, dO, lse, delta, N, C, H, scale, dqkv, st, st2); break;
+        default: if constexpr (HD >= 16) launch_bwd_rw<HD, 2>(qkv, dO, lse, delta, N, C, H, scale, dqkv, st, st2);
+                 else launch_bwd_rw<HD, 4>(qkv, dO, lse, delta, N, C, H, scale, dqkv, st, st2);
     }
+}
+
+// Side streams + events for the fork/join inside moma_attn_bwd (created once per process; no device memory).
+struct BwdStreams {
+    cudaStream_t s1 = nullptr, s2 = nullptr;
+    cudaEvent_t fork = nullptr, d_o = nullptr, dq = nullptr, dkv = nullptr, join1 = nullptr, join2 = nullptr;
+    bool ok = false;
+};
+static BwdStreams& bwd_streams() {
+    static BwdStreams b;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        bool good = cudaStreamCreateWithFlags(&b.s1, cudaStreamNonBlocking) == cudaSuccess &&
+                    cudaStreamCreateWithFlags(&b.s2, cudaStreamNonBlocking) == cudaSuccess;
+        cudaEvent_t* evs[] = {&b.fork, &b.d_o, &b.dq, &b.dkv, &b.join1, &b.join2};
+        for (auto e : evs) good = good && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
+        b.ok = good;
+        if (!good) cudaGetLastError();
+    }
+    return b;
 }
 
 static int check_attn(const char* who, int64_t N, int64_t C, int H) {
@@ -640,22 +662,38 @@ extern "C" __attribute__((visibility("default"))) int moma_attn_bwd(const float*
     float* dO = static_cast<float*>(workspace);
     float* dqkv = dO + N * C;
     float* delta = dqkv + N * 3 * C;
+    // The backward is a small DAG, not a chain: fork it over two side streams (captured as parallel branches
+    // by a CUDA graph) so only  dO -> delta -> dQ || dK,dV -> dx  stays on the critical path.
+    //   s1: dW_proj, db_proj          (need only dy, o)
+    //   st: dO, delta, dQ, dx         s2: dK/dV, then dW_qkv, db_qkv (after dQ)
+    BwdStreams& bs = bwd_streams();
+    cudaStream_t s1 = bs.ok ? bs.s1 : st, s2 = bs.ok ? bs.s2 : st;
+    if (bs.ok) { cudaEventRecord(bs.fork, st); cudaStreamWaitEvent(s1, bs.fork, 0); }
     // proj backward: dW_proj[co, ci] = sum_n dy[n, co] o[n, ci];  db = colsum(dy);  dO = dy W_proj
-    if (grad_w_proj) sgemm(grad_y, 1, C, o, 1, C, nullptr, grad_w_proj, C, c, c, n, st);
-    if (grad_b_proj) colsum_kernel<<<(c + 31) / 32, 256, 0, st>>>(grad_y, n, c, grad_b_proj);
+    if (grad_w_proj) sgemm(grad_y, 1, C, o, 1, C, nullptr, grad_w_proj, C, c, c, n, s1);
+    if (grad_b_proj) colsum_kernel<<<(c + 31) / 32, 256, 0, s1>>>(grad_y, n, c, grad_b_proj);
     sgemm(grad_y, C, 1, w_proj, 1, C, nullptr, dO, C, n, c, c, st);
     attn_delta_kernel<<<(n * H + 3) / 4, 128, 0, st>>>(dO, o, n, c, H, delta);
+    if (bs.ok) { cudaEventRecord(bs.d_o, st); cudaStreamWaitEvent(s2, bs.d_o, 0); }
     switch (hd) {
-        case 8: launch_bwd<8>(qkv, dO, lse, delta, n, c, H, scale, dqkv, st); break;
-        case 16: launch_bwd<16>(qkv, dO, lse, delta, n, c, H, scale, dqkv, st); break;
-        case 32: launch_bwd<32>(qkv, dO, lse, delta, n, c, H, scale, dqkv, st); break;
-        case 64: launch_bwd<64>(qkv, dO, lse, delta, n, c, H, scale, dqkv, st); break;
-        default: launch_bwd<128>(qkv, dO, lse, delta, n, c, H, scale, dqkv, st); break;
+        case 8: launch_bwd<8>(qkv, dO, lse, delta, n, c, H, scale, dqkv, st, s2); break;
+        case 16: launch_bwd<16>(qkv, dO, lse, delta, n, c, H, scale, dqkv, st, s2); break;
+        case 32: launch_bwd<32>(qkv, dO, lse, delta, n, c, H, scale, dqkv, st, s2); break;
+        case 64: launch_bwd<64>(qkv, dO, lse, delta, n, c, H, scale, dqkv, st, s2); break;
+        default: launch_bwd<128>(qkv, dO, lse, delta, n, c, H, scale, dqkv, st, s2); break;
+    }
+    if (bs.ok) {
+        cudaEventRecord(bs.dq, st);  cudaStreamWaitEvent(s2, bs.dq, 0);     // s2 now has dQ and dK/dV
+        cudaEventRecord(bs.dkv, s2); cudaStreamWaitEvent(st, bs.dkv, 0);    // st too
     }
     // qkv backward: dW_qkv[j, ci] = sum_n dqkv[n, j] x[n, ci]; db = colsum(dqkv); dx = dqkv W_qkv
-    if (grad_w_qkv) sgemm(dqkv, 1, 3 * C, x, 1, C, nullptr, grad_w_qkv, C, 3 * c, c, n, st);
-    if (grad_b_qkv) colsum_kernel<<<(3 * c + 31) / 32, 256, 0, st>>>(dqkv, n, 3 * c, grad_b_qkv);
+    if (grad_w_qkv) sgemm(dqkv, 1, 3 * C, x, 1, C, nullptr, grad_w_qkv, C, 3 * c, c, n, s2);
+    if (grad_b_qkv) colsum_kernel<<<(3 * c + 31) / 32, 256, 0, s2>>>(dqkv, n, 3 * c, grad_b_qkv);
     if (grad_x) sgemm(dqkv, 3 * C, 1, w_qkv, 1, C, nullptr, grad_x, C, n, c, 3 * c, st);
+    if (bs.ok) {                                                             // join
+        cudaEventRecord(bs.join1, s1); cudaStreamWaitEvent(st, bs.join1, 0);
+        cudaEventRecord(bs.join2, s2); cudaStreamWaitEvent(st, bs.join2, 0);
+    }
     MOMA_CUDA_LAUNCH_CHECK("attn_bwd");
     note_launches(4 + (grad_w_proj != nullptr) + (grad_b_proj != nullptr) + (grad_w_qkv != nullptr) +
                   (grad_b_qkv != nullptr) + (grad_x != nullptr));
