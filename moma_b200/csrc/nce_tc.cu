@@ -511,6 +511,11 @@ __device__ __forceinline__ float ex2_poly(float x) {
 constexpr bool kPolyExp = false;
 __device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
+#ifdef MOMA_TC_ABLATE
+constexpr bool kAblateHooks = true;
+#else
+constexpr bool kAblateHooks = false;
+#endif
 constexpr int kStages2 = 5;     // queue-tile ring depth of the v2 kernel
 constexpr int kSBuf = 3;        // score buffers in TMEM: S(i+1), S(i+2) are ready while softmax works on S(i)
 
@@ -549,8 +554,10 @@ __global__ void __launch_bounds__(384, 1)
 nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                int B, long long K_local, float scale_log2, int n_splits, float* __restrict__ part_m,
                float* __restrict__ part_l, float* __restrict__ part_mmax, float* __restrict__ part_O,
-               float* __restrict__ dbg_S) {
+               float* __restrict__ dbg_S, int ablate_arg) {
     using C = Cfg2<D>;
+    // timing ablations (scripts/ablate_nce.py); compiled out of the product library
+    const int ablate = kAblateHooks ? ablate_arg : 0;
     constexpr int BN = C::BN;
     extern __shared__ uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -591,7 +598,7 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         tma_prefetch_desc(&tmap_k);
         mbar_init(b_q_full, 1);
         for (int s = 0; s < kStages2; ++s) { mbar_init(b_kv_full(s), 1); mbar_init(b_kv_empty(s), 1); }
-        for (int b = 0; b < kSBuf; ++b) { mbar_init(b_s_full(b), 1); mbar_init(b_p_full(b), 256); mbar_init(b_pv_done(b), 1); }
+        for (int b = 0; b < kSBuf; ++b) { mbar_init(b_s_full(b), 1); mbar_init(b_p_full(b), 8); mbar_init(b_pv_done(b), 1); }
         mbar_init(b_o_final, 1);
         fence_barrier_init();
     }
@@ -611,6 +618,7 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             for (int i = 0; i < nt; ++i) {
                 const int s = i % kStages2;
                 mbar_wait(b_kv_empty(s), ((i / kStages2) & 1) ^ 1, 301);
+                if (ablate & 64) { mbar_expect_tx(b_kv_full(s), 0); continue; }
                 mbar_expect_tx(b_kv_full(s), C::K_TILE);
                 for (int kb = 0; kb < C::KB; ++kb)
                     tma_load_2d(kv_smem + s * C::K_TILE + kb * C::K_BLOCK, &tmap_k, kb * 64, (t0 + i) * BN, b_kv_full(s));
@@ -627,7 +635,7 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             auto issue_s = [&](int b, int stage) {
                 const uint64_t db0 = k_desc0 + (uint64_t)((stage * C::K_TILE) >> 4);
 #pragma unroll 1
-                for (int ks = 0; ks < D / 16; ++ks) {
+                for (int ks = 0; ks < ((ablate & 8) ? 0 : D / 16); ++ks) {
                     const uint32_t qoff = (uint32_t)((ks >> 2) * C::Q_BLOCK + (ks & 3) * 32) >> 4;
                     const uint32_t koff = (uint32_t)((ks >> 2) * C::K_BLOCK + (ks & 3) * 32) >> 4;
                     umma_ss(s_colf(b), q_desc0 + qoff, db0 + koff, idesc_s, ks > 0 ? 1u : 0u);
@@ -637,7 +645,7 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             auto issue_pv = [&](int b, int stage, bool accumulate) {
                 const uint64_t db0 = v_desc0 + (uint64_t)((stage * C::K_TILE) >> 4);
 #pragma unroll 1
-                for (int ks = 0; ks < BN / 16; ++ks)
+                for (int ks = 0; ks < ((ablate & 4) ? 0 : BN / 16); ++ks)
                     umma_ts(tmem + C::O_COL, s_colf(b) + ks * 8, db0 + (uint64_t)(ks * (2048 >> 4)), idesc_o,
                             (accumulate || ks > 0) ? 1u : 0u);
                 umma_commit(b_pv_done(b));
@@ -647,20 +655,32 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             tc_fence_after();
             issue_s(0, 0);
             for (int j = 1; j < kSBuf && j < nt; ++j) { mbar_wait(b_kv_full(j), 0, 306); tc_fence_after(); issue_s(j, j); }
+            long long* tr = ((ablate & 256) && dbg_S != nullptr && mt == 0 && split == 0)
+                                ? reinterpret_cast<long long*>(dbg_S + 2ll * B * 128) : nullptr;
+            if (tr) tr[0] = clock64();
+            int* tri = ((ablate & 512) && tr) ? reinterpret_cast<int*>(tr) + 64 + 2048 : nullptr;
+#define IS_STAMP(k) if (tri && i >= 64 && i < 80) tri[(i - 64) * 8 + (k)] = (int)clock()
             for (int i = 0; i < nt; ++i) {
                 const int st = i % kStages2, b = i % kSBuf;
+                IS_STAMP(0);
                 mbar_wait(b_p_full(b), (i / kSBuf) & 1, 304);
                 tc_fence_after();
+                IS_STAMP(1);
                 issue_pv(b, st, i > 0);
                 umma_commit(b_kv_empty(st));
+                IS_STAMP(2);
                 if (i + kSBuf < nt) {
                     const int sn = (i + kSBuf) % kStages2;
                     mbar_wait(b_kv_full(sn), ((i + kSBuf) / kStages2) & 1, 305);
                     tc_fence_after();
+                    IS_STAMP(3);
                     issue_s(b, sn);
+                    IS_STAMP(4);
                 }
             }
+#undef IS_STAMP
             umma_commit(b_o_final);
+            if (tr) { tr[1] = clock64(); tr[2] = nt; }
         }
     } else if (warp >= 4) {
         // ===================================================== softmax (two column halves)
@@ -675,17 +695,25 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const bool ragged_last = (K_local % BN) != 0;
         const float2 sc2 = make_float2(scale_log2, scale_log2);
 
+        int* trs = ((ablate & 512) && dbg_S != nullptr && mt == 0 && split == 0 && (warp == 4 || warp == 8) && lane == 0)
+                       ? reinterpret_cast<int*>(dbg_S + 2ll * B * 128) + 64 + (warp == 8 ? 1024 : 0) : nullptr;
+#define SM_STAMP(k) if (trs && i >= 64 && i < 80) trs[(i - 64) * 8 + (k)] = (int)clock()
         for (int i = 0; i < nt; ++i) {
             const int b = i % kSBuf;
+            SM_STAMP(0);
             mbar_wait(b_s_full(b), (i / kSBuf) & 1, 401);
             tc_fence_after();
+            SM_STAMP(1);
             uint32_t v[64];
-            {
+            if (ablate & 2) {
+#pragma unroll
+                for (int j = 0; j < 64; ++j) { v[j] = 0x3c000000u + j; asm volatile("" : "+r"(v[j])); }
+            } else {
                 uint32_t* v0 = v; uint32_t* v1 = v + 32;
                 TMEM_LD32(s_colf(b) + lane_off + half * 64, v0);
                 TMEM_LD32(s_colf(b) + lane_off + half * 64 + 32, v1);
+                tmem_wait_ld();
             }
-            tmem_wait_ld();
             if (dbg_S != nullptr && i == 0 && split == 0 && row < B) {
 #pragma unroll
                 for (int j = 0; j < 64; ++j) dbg_S[(long long)row * BN + half * 64 + j] = __uint_as_float(v[j]);
@@ -696,6 +724,7 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 for (int j = 0; j < 64; ++j)
                     if (j >= valid) v[j] = __float_as_uint(-CUDART_INF_F);
             }
+            SM_STAMP(2);
             float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
 #pragma unroll
             for (int j = 0; j < 64; j += 4) {
@@ -703,10 +732,13 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 mx1 = fmaxf(fmaxf(mx1, __uint_as_float(v[j + 2])), __uint_as_float(v[j + 3]));
             }
             // exchange the half-row maxima with the thread holding the other 64 columns of this row
-            bars->xch[i & 1][half][rit] = fmaxf(mx0, mx1);
-            pair_barrier(1 + wq);
-            const float mx = fmaxf(fmaxf(mx0, mx1), bars->xch[i & 1][half ^ 1][rit]) * scale_log2;
+            if (!(ablate & 32)) {
+                bars->xch[i & 1][half][rit] = fmaxf(mx0, mx1);
+                pair_barrier(1 + wq);
+            }
+            const float mx = (ablate & 32) ? 0.f : fmaxf(fmaxf(mx0, mx1), bars->xch[i & 1][half ^ 1][rit]) * scale_log2;
             m_true = fmaxf(m_true, mx);
+            SM_STAMP(3);
             const bool need = mx > m_ref + kLazyTau;                 // identical in both halves of the row
             if (i > 0 && __any_sync(0xffffffffu, need)) {
                 mbar_wait(b_pv_done((i - 1) % kSBuf), ((i - 1) / kSBuf) & 1, 402);
@@ -733,20 +765,29 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 for (int j = 0; j < 32; j += 4) {
                     const float2 x01 = ffma2(make_float2(__uint_as_float(v[32 * c + j]), __uint_as_float(v[32 * c + j + 1])), sc2, ng2);
                     const float2 x23 = ffma2(make_float2(__uint_as_float(v[32 * c + j + 2]), __uint_as_float(v[32 * c + j + 3])), sc2, ng2);
-                    const float2 p01 = make_float2(ex2(x01.x), ex2(x01.y));
-                    const float2 p23 = make_float2(ex2(x23.x), kPolyExp ? ex2_poly(x23.y) : ex2(x23.y));
+                    float2 p01 = x01, p23 = x23;
+                    if (!(ablate & 1)) {
+                        p01 = make_float2(ex2(x01.x), ex2(x01.y));
+                        p23 = make_float2(ex2(x23.x), kPolyExp ? ex2_poly(x23.y) : ex2(x23.y));
+                    }
                     l2a = fadd2(l2a, p01);
                     l2b = fadd2(l2b, p23);
                     pk[j >> 1] = pack_bf16(p01.x, p01.y);
                     pk[(j >> 1) + 1] = pack_bf16(p23.x, p23.y);
                 }
                 // P (bf16 pairs) aliases the S buffer: half h owns packed columns [32h, 32h + 32)
-                TMEM_ST16(s_colf(b) + lane_off + half * 32 + 16 * c, pk);
+                if (!(ablate & 16)) TMEM_ST16(s_colf(b) + lane_off + half * 32 + 16 * c, pk);
+                else if (pk[3] == 0x12345678u) bars->lsum[rit] = 0.f;      // keep the packs alive
             }
+            SM_STAMP(4);
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(b_p_full(b));
+            __syncwarp();
+            SM_STAMP(5);
+            if (lane == 0) mbar_arrive(b_p_full(b));          // one arrival per warp: 8 instead of 256 smem atomics
+            SM_STAMP(6);
         }
+#undef SM_STAMP
 
         // epilogue: O (TMEM) -> part_O (each half writes its D/2 columns), stats by half 0
         const float l_half = (l2a.x + l2a.y) + (l2b.x + l2b.y);
@@ -864,8 +905,10 @@ static int launch2(const void* q, const void* queue, int64_t B, int64_t K_local,
     }
     const dim3 grid((unsigned)((B + kBM - 1) / kBM), (unsigned)n_splits);
     const float scale_log2 = inv_T * 1.4426950408889634f;
+    int ablate = 0;
+    if (kAblateHooks) { const char* e = getenv("MOMA_TC_ABLATE"); ablate = e ? atoi(e) : 0; }
     nce_tc2_kernel<D><<<grid, C::THREADS, C::SMEM_TOTAL, st>>>(mq, mk, (int)B, (long long)K_local, scale_log2, n_splits,
-                                                              pm, pl, pmm, pO, dbg);
+                                                              pm, pl, pmm, pO, dbg, ablate);
     MOMA_CUDA_LAUNCH_CHECK("nce_partial(bf16/tcgen05 v2)");
     note_launches(1);
     return MOMA_OK;
