@@ -192,6 +192,27 @@ int moma_attn_bwd(const float *x, const float *w_qkv, const float *w_proj, const
                   moma_stream_t stream);
 
 /* ------------------------------------------------------------------------- *
+ * Projection-head Linear (+ReLU) -- replaces the nn.Linear / nn.ReLU layers of
+ * embed_s / embed_t (MoMA/criterion_moco_att.py:254-305) and their autograd.
+ *   y[M, N] = act(x[M, K] . w[N, K]^T + b[N]),  act = ReLU when relu != 0;  b nullable.
+ * Tensor-core GEMM in 3xTF32 (error-compensated TF32 split, fp32-level accuracy,
+ * fp32 accumulation); deterministic split-K through the caller-owned workspace.
+ * Workspace: moma_linear_workspace_bytes(M, N, K) bytes, 16-byte aligned, ZEROED
+ * once before its first use (its ticket counters are left zero by every call);
+ * one workspace per concurrently running call.  NULL workspace = no split-K.
+ * Backward: y is the forward output (the ReLU mask; may be NULL when relu == 0);
+ * any of grad_x [M, K], grad_w [N, K], grad_b [N] may be NULL; overwritten, not
+ * accumulated.
+ * ------------------------------------------------------------------------- */
+size_t moma_linear_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int moma_linear_fwd(const float *x, const float *w, const float *b, int64_t M, int64_t N, int64_t K,
+                    int relu, float *y, void *workspace, size_t workspace_bytes,
+                    moma_stream_t stream);
+int moma_linear_bwd(const float *x, const float *w, const float *y, const float *grad_y, int64_t M,
+                    int64_t N, int64_t K, int relu, float *grad_x, float *grad_w, float *grad_b,
+                    void *workspace, size_t workspace_bytes, moma_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
  * debug / test hooks (not used by the product path)
  * moma_debug_nce_tc: the tcgen05 partial kernel with an optional dump of the raw
  *   score tile S = Q . Tile^T of the first queue tile of split 0:

@@ -8,6 +8,8 @@ GEMMs, outside the rewritten path -- SURVEY 8a a11).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -172,21 +174,42 @@ class Attention2(nn.Module):
 class _Head(nn.Sequential):
     """Projection head (same sub-module indices / state_dict keys as the reference's nn.Sequential).
 
-    In bf16 mode a head evaluated WITHOUT autograd -- the momentum teacher's ``embed_t`` inside
-    ``_shuffle_bn`` (learning/contrast_trainer.py:117-121) -- runs its Linear layers with TF32 tensor-core
-    GEMMs: no gradient flows through it and its output is rounded to bf16 by the InfoNCE kernel anyway
-    (measured end-to-end effect 5e-5 on the gradients, scripts/tf32_heads_error.py).  With autograd
-    (the student's ``embed_s``) and in fp32 mode the GEMMs stay IEEE FP32, as in the reference."""
+    On the GPU every ``nn.Linear`` (+ the ``nn.ReLU`` that follows it) runs as one ``moma_linear_fwd`` launch --
+    3xTF32 tensor-core GEMM with the bias / ReLU epilogue fused, fp32-level accuracy -- and back-propagates
+    through ``moma_linear_bwd``.  One exception: in bf16 mode a LARGE layer evaluated WITHOUT autograd (the
+    momentum teacher's ``embed_t`` inside ``_shuffle_bn``, learning/contrast_trainer.py:117-121) uses a
+    single-pass TF32 library GEMM: no gradient flows through it and its output is rounded to bf16 by the InfoNCE
+    kernel anyway (measured end-to-end effect 5e-5 on the gradients, scripts/tf32_heads_error.py)."""
+
+    _TF32_MIN_WEIGHT = 1 << 20          # elements; below this the 3xTF32 kernel is as fast as the library call
+
+    def _tf32_library(self, lin):
+        return (not torch.is_grad_enabled() and ops.get_precision() == "bf16"
+                and lin.weight.numel() >= self._TF32_MIN_WEIGHT)
 
     def forward(self, x):
-        if torch.is_grad_enabled() or ops.get_precision() != "bf16" or not x.is_cuda:
+        if not x.is_cuda or os.environ.get("MOMA_B200_GEMM") == "simt":
             return super().forward(x)
-        prev = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = True
-        try:
-            return super().forward(x)
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = prev
+        mods = list(self)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, nn.Linear) and x.dim() == 2:
+                if self._tf32_library(m):
+                    prev = torch.backends.cuda.matmul.allow_tf32
+                    torch.backends.cuda.matmul.allow_tf32 = True
+                    try:
+                        x = m(x)
+                    finally:
+                        torch.backends.cuda.matmul.allow_tf32 = prev
+                else:
+                    relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+                    x = ops.linear(x, m.weight, m.bias, relu=relu, key=id(m))
+                    i += 1 if relu else 0
+            else:
+                x = m(x)
+            i += 1
+        return x
 
 
 def _head(kind, in_dim, feat_dim):

@@ -1,6 +1,7 @@
 // C-ABI plumbing: version, error string, device probe.
 #include <stdarg.h>
 #include "common.cuh"
+#include <stdlib.h>
 
 #include <atomic>
 namespace moma {
@@ -16,6 +17,10 @@ void set_error(const char* fmt, ...) {
 int fail(int code, const char* fmt, ...) {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
     return code;
+}
+bool use_simt_gemm() {
+    static const bool simt = [] { const char* e = getenv("MOMA_B200_GEMM"); return e != nullptr && std::string(e) == "simt"; }();
+    return simt;
 }
 int sm_count() {
     static int cached[64] = {0};

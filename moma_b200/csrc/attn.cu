@@ -113,6 +113,10 @@ static void sgemm_tm(const float* A, int64_t a_rs, int64_t a_cs, const float* Bm
 static void sgemm(const float* A, int64_t a_rs, int64_t a_cs, const float* Bm, int64_t b_rs,
                   int64_t b_cs, const float* bias, float* Cm, int64_t ldc, int M, int N, int K,
                   cudaStream_t st) {
+    if (!use_simt_gemm()) {      // tensor-core path (3xTF32, gemm.cu); single split: no workspace here
+        gemm_nt(A, nullptr, a_rs, a_cs, Bm, b_rs, b_cs, bias, Cm, ldc, M, N, K, 0, nullptr, 0, st);
+        return;
+    }
     const int ctas32 = ((N + kGN - 1) / kGN) * ((M + 31) / 32);
     if (ctas32 >= sm_count() * 3 / 4) sgemm_tm<32>(A, a_rs, a_cs, Bm, b_rs, b_cs, bias, Cm, ldc, M, N, K, st);
     else sgemm_tm<16>(A, a_rs, a_cs, Bm, b_rs, b_cs, bias, Cm, ldc, M, N, K, st);

@@ -32,6 +32,15 @@ inline cudaStream_t as_stream(moma_stream_t s) { return reinterpret_cast<cudaStr
 int sm_count();
 void note_launches(int n);   // launch counter behind moma_debug_launch_count()   // cached multiprocessor count of the current device (148 on B200)
 
+// gemm.cu: C[M,N] = act(A B^T + bias) on the tensor cores (3xTF32); see the file header for the operand convention
+int gemm_splits(int M, int N, int K);
+size_t gemm_workspace_bytes(int M, int N, int K);
+int gemm_nt(const float* A, const float* a_mask, int64_t a_rs, int64_t a_cs, const float* Bm, int64_t b_rs, int64_t b_cs,
+            const float* bias, float* C, int64_t ldc, int M, int N, int K, int relu, void* workspace, size_t workspace_bytes,
+            cudaStream_t st);
+void colsum_masked(const float* X, const float* mask, int rows, int cols, float* out, cudaStream_t st);
+bool use_simt_gemm();        // MOMA_B200_GEMM=simt: IEEE-FP32 CUDA-core GEMMs instead (A/B switch, read once)
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

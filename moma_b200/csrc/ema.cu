@@ -4,6 +4,7 @@
 // One launch walks a chunk table covering every parameter tensor; 128-bit
 // streaming loads/stores; exactly the reference's two fp32 roundings.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace moma {
 
@@ -24,10 +25,15 @@ __device__ __forceinline__ float ema1(float d, float s, float m, float a) {
     return __fmaf_rn(a, s, __fmul_rn(d, m));
 }
 
+// Persistent: a few CTAs per SM walk the chunk table with a grid stride.  Each thread keeps 16 independent 128-bit
+// loads in flight (64 KB per CTA), which is enough to saturate HBM from ~1-2 CTAs per SM -- and it leaves the rest of
+// every SM free, so the latency-bound kernels of the criterion step that run concurrently (other graph branches)
+// get their CTAs scheduled at once instead of queueing behind a full-occupancy streaming grid.
 __global__ void __launch_bounds__(kEmaThreads)
-ema_multi_kernel(const EmaChunk* __restrict__ table, float m, float a) {
-    const EmaChunk c = table[blockIdx.x];
+ema_multi_kernel(const EmaChunk* __restrict__ table, int n_chunks, float m, float a) {
     const int t = threadIdx.x;
+  for (int ci = blockIdx.x; ci < n_chunks; ci += gridDim.x) {
+    const EmaChunk c = table[ci];
     if (c.vec_ok) {
         const int nvec = c.count >> 2;
         const float4* s4 = reinterpret_cast<const float4*>(c.src);
@@ -53,6 +59,12 @@ ema_multi_kernel(const EmaChunk* __restrict__ table, float m, float a) {
     } else {
         for (int i = t; i < c.count; i += kEmaThreads) c.dst[i] = ema1(c.dst[i], c.src[i], m, a);
     }
+  }
+}
+
+static int ema_ctas_per_sm() {
+    static const int v = [] { const char* e = getenv("MOMA_B200_EMA_CTAS_PER_SM"); int n = e ? atoi(e) : 2; return n < 1 ? 1 : (n > 8 ? 8 : n); }();
+    return v;
 }
 
 }  // namespace moma
@@ -107,8 +119,10 @@ extern "C" __attribute__((visibility("default"))) int moma_ema_multi(const void*
     if (n_chunks == 0) return MOMA_OK;
     MOMA_REQUIRE(dev_table && aligned16(dev_table), MOMA_ERR_ALIGN, "ema_multi: table null/unaligned");
     MOMA_REQUIRE(n_chunks < (1ll << 31), MOMA_ERR_UNSUPPORTED, "ema_multi: too many chunks");
-    ema_multi_kernel<<<(unsigned)n_chunks, kEmaThreads, 0, as_stream(stream)>>>(
-        static_cast<const EmaChunk*>(dev_table), m, one_minus_m);
+    int64_t grid = (int64_t)sm_count() * ema_ctas_per_sm();
+    if (grid > n_chunks) grid = n_chunks;
+    ema_multi_kernel<<<(unsigned)grid, kEmaThreads, 0, as_stream(stream)>>>(
+        static_cast<const EmaChunk*>(dev_table), (int)n_chunks, m, one_minus_m);
     MOMA_CUDA_LAUNCH_CHECK("ema_multi");
     note_launches(1);
     return MOMA_OK;

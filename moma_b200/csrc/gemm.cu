@@ -1,0 +1,400 @@
+// Small-matrix GEMM for the projection heads and the attention projections of the MoMA criterion:
+//   C[M, N] = act( A · B^T + bias ),  A[m, k] = A[m * a_rs + k * a_cs],  B[n, k] = B[n * b_rs + k * b_cs].
+//
+// The matrices of this path are tiny (M = batch = 256 rows, N, K <= 2048), so a launch is bound by latency and
+// by how many SMs it reaches, not by arithmetic: 32 x 32 output tiles (every tile its own CTA), split along K
+// when the tile grid would not fill the 148 SMs, the next K-slab in flight in registers while the current one
+// is multiplied.  The products run on the tensor cores as 3xTF32 (a = a_hi + a_lo, both TF32; a·b ~=
+// a_lo·b_hi + a_hi·b_lo + a_hi·b_hi accumulated in fp32), which keeps fp32-level accuracy (the dropped a_lo·b_lo term
+// is 2^-22 relative) -- a single TF32 pass is NOT accurate enough for the student's gradients (scripts/tf32_heads_error.py).
+// Warp-level mma.sync is deliberate here: a 32 x 32 x K tile has no use for a 128-row tcgen05 accumulator.
+//
+// Split-K is deterministic: every split writes its partial tile to the workspace, takes a ticket, and the last
+// arrival sums the partials in split order, applies bias / ReLU and writes C (the ticket counter resets itself).
+#include "common.cuh"
+
+namespace moma {
+
+namespace {
+
+constexpr int kTM = 32, kTN = 32, kTK = 32, kThreads = 128;
+constexpr int kLdK = kTK + 4;        // [row][k] tiles: 36-float rows  -> fragment reads hit banks 4g + t
+constexpr int kLdR = kTM + 8;        // [k][row] tiles: 40-float rows  -> fragment reads hit banks 8t + g
+constexpr int kTile = kTK * kLdR;    // floats per operand tile (the larger of the two layouts)
+constexpr int kStages = 3;
+constexpr int kMaxSplits = 16;
+
+// x = hi + lo with hi = x rounded to TF32 (10-bit mantissa, round-to-nearest on the bit pattern: integer add of half an
+// ulp, then mask) and lo = x - hi (exact in fp32).  The tensor core reads only the top 19 bits of lo, i.e. truncates it:
+// |error| <= 2^-21 |x|, unbiased because lo's sign is.  Three ALU/FMA-pipe instructions per element.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__device__ __forceinline__ void cp_async16(float* dst, const float* src, bool valid) {
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* dst, const float* src, bool valid) {
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(valid ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// operand access pattern of a [rows, K] operand
+enum : int { kVecK = 0,    // k contiguous (cs == 1), 16-byte aligned rows: 16-byte copies along k, tile kept [row][k]
+             kVecR = 1,    // row index contiguous (rs == 1): 16-byte copies along the rows, tile kept [k][row]
+             kScalar = 2 };// anything else: 4-byte copies, tile kept [row][k]
+
+struct Operand {
+    const float* p;
+    int64_t rs, cs;
+    int rows, mode;
+};
+
+// global -> shared, asynchronously (zero-filled outside the matrix): one 32 x 32 tile, 8 floats per thread
+__device__ __forceinline__ void issue_tile(float* dst, const float* __restrict__ src, const Operand& op, int row0, int k0, int K) {
+    const int tid = threadIdx.x;
+    if (op.mode == kVecK) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int idx = tid + i * kThreads, rr = idx >> 3, kv = (idx & 7) * 4;
+            const bool ok = row0 + rr < op.rows && k0 + kv < K;
+            cp_async16(dst + rr * kLdK + kv, ok ? src + (int64_t)(row0 + rr) * op.rs + k0 + kv : src, ok);
+        }
+    } else if (op.mode == kVecR) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int idx = tid + i * kThreads, kk = idx >> 3, rv = (idx & 7) * 4;
+            const bool ok = k0 + kk < K && row0 + rv < op.rows;
+            cp_async16(dst + kk * kLdR + rv, ok ? src + (int64_t)(k0 + kk) * op.cs + row0 + rv : src, ok);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int idx = tid + i * kThreads, rr = idx >> 5, kk = idx & 31;
+            const bool ok = row0 + rr < op.rows && k0 + kk < K;
+            cp_async4(dst + rr * kLdK + kk, ok ? src + (int64_t)(row0 + rr) * op.rs + (int64_t)(k0 + kk) * op.cs : src, ok);
+        }
+    }
+}
+
+struct GemmParams {
+    Operand a, b;
+    const float* a_mask;       // optional, indexed like A: elements with mask <= 0 read as 0 (ReLU backward)
+    const float* bias;
+    float* C;
+    int64_t ldc;
+    int M, N, K, relu, splits;
+    float* partial;            // [splits, M, N] when splits > 1
+    unsigned int* tickets;     // one per output tile, zero between launches
+};
+
+template <bool MASK>
+__global__ void __launch_bounds__(kThreads)
+gemm3xtf32_kernel(const GemmParams p) {
+    __shared__ __align__(16) float sA[kStages][kTile];
+    __shared__ __align__(16) float sB[kStages][kTile];
+    __shared__ __align__(16) float sM[MASK ? kStages : 1][MASK ? kTile : 4];
+    __shared__ int s_last;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = (warp >> 1) * 16, wn = (warp & 1) * 16;
+    const int m0 = blockIdx.y * kTM, n0 = blockIdx.x * kTN;
+    const int ktiles = (p.K + kTK - 1) / kTK;
+    const int kt0 = (int)((long long)ktiles * blockIdx.z / p.splits);
+    const int kt1 = (int)((long long)ktiles * (blockIdx.z + 1) / p.splits);
+    // shared-memory strides of the two tile layouts
+    const int a_sr = p.a.mode == kVecR ? 1 : kLdK, a_sk = p.a.mode == kVecR ? kLdR : 1;
+    const int b_sr = p.b.mode == kVecR ? 1 : kLdK, b_sk = p.b.mode == kVecR ? kLdR : 1;
+    const int a_base = (wm + g) * a_sr + t * a_sk;
+    const int b_base = (wn + g) * b_sr + t * b_sk;
+
+    auto issue = [&](int stage, int kt) {
+        issue_tile(sA[stage], p.a.p, p.a, m0, kt * kTK, p.K);
+        issue_tile(sB[stage], p.b.p, p.b, n0, kt * kTK, p.K);
+        if (MASK) issue_tile(sM[stage], p.a_mask, p.a, m0, kt * kTK, p.K);
+    };
+#pragma unroll
+    for (int s = 0; s < kStages - 1; ++s) {
+        if (kt0 + s < kt1) issue(s, kt0 + s);
+        cp_async_commit();
+    }
+
+    float acc[2][4] = {};
+    for (int kt = kt0; kt < kt1; ++kt) {
+        const int st = (kt - kt0) % kStages;
+        cp_async_wait<kStages - 2>();
+        __syncthreads();                      // slab kt has landed for everyone; slab kt - 1's buffer is free again
+        if (kt + kStages - 1 < kt1) issue((kt - kt0 + kStages - 1) % kStages, kt + kStages - 1);
+        cp_async_commit();
+        const float* A = sA[st];
+        const float* Bt = sB[st];
+        const float* Mk = sM[MASK ? st : 0];
+        // The tensor core adds into its accumulator with truncation, so a long chain drifts (measured 2.5e-6
+        // relative at K = 512 against 2e-7 for slab-long chains): accumulate one slab, then add it to the running
+        // sum with an ordinary round-to-nearest FADD.
+        // Separate accumulators for the three product terms: six independent MMA chains per warp instead of two
+        // three-deep dependent ones (mma.sync latency ~50 clk against ~9 clk issue).
+        float plh[2][4] = {}, phl[2][4] = {}, phh[2][4] = {};
+#pragma unroll
+        for (int kk = 0; kk < kTK; kk += 8) {
+            uint32_t ah[4], al[4];
+            const int ia = a_base + kk * a_sk;
+            float x[4] = {A[ia], A[ia + 8 * a_sr], A[ia + 4 * a_sk], A[ia + 8 * a_sr + 4 * a_sk]};
+            if (MASK) {
+                x[0] = Mk[ia] > 0.f ? x[0] : 0.f;                       x[1] = Mk[ia + 8 * a_sr] > 0.f ? x[1] : 0.f;
+                x[2] = Mk[ia + 4 * a_sk] > 0.f ? x[2] : 0.f;            x[3] = Mk[ia + 8 * a_sr + 4 * a_sk] > 0.f ? x[3] : 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split_tf32(x[e], ah[e], al[e]);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int ib = b_base + 8 * j * b_sr + kk * b_sk;
+                uint32_t bh[2], bl[2];
+                split_tf32(Bt[ib], bh[0], bl[0]);
+                split_tf32(Bt[ib + 4 * b_sk], bh[1], bl[1]);
+                mma_tf32(plh[j], al, bh);
+                mma_tf32(phl[j], ah, bl);
+                mma_tf32(phh[j], ah, bh);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[j][e] += (plh[j][e] + phl[j][e]) + phh[j][e];     // small terms first
+    }
+    cp_async_wait<0>();
+
+    // accumulator fragment: acc[j][0..1] -> row wm + g, cols wn + 8j + 2t (+1); acc[j][2..3] -> row + 8
+    auto finish = [&](int r, int c, float v0, float v1) {
+        if (r >= p.M) return;
+        if (p.bias) { if (c < p.N) v0 += p.bias[c]; if (c + 1 < p.N) v1 += p.bias[c + 1]; }
+        if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+        float* dst = p.C + (int64_t)r * p.ldc + c;
+        if (c + 1 < p.N && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
+        else { if (c < p.N) dst[0] = v0; if (c + 1 < p.N) dst[1] = v1; }
+    };
+    if (p.splits == 1) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int c = n0 + wn + 8 * j + 2 * t;
+            finish(m0 + wm + g, c, acc[j][0], acc[j][1]);
+            finish(m0 + wm + g + 8, c, acc[j][2], acc[j][3]);
+        }
+        return;
+    }
+    // ---- split-K: publish the partial tile, last arrival reduces in split order
+    {
+        float* mine = p.partial + (int64_t)blockIdx.z * p.M * p.N;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int c = n0 + wn + 8 * j + 2 * t;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = m0 + wm + g + 8 * h;
+                if (r < p.M) {
+                    if (c < p.N) __stcg(mine + (int64_t)r * p.N + c, acc[j][2 * h]);
+                    if (c + 1 < p.N) __stcg(mine + (int64_t)r * p.N + c + 1, acc[j][2 * h + 1]);
+                }
+            }
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    const unsigned tile = blockIdx.y * gridDim.x + blockIdx.x;
+    if (tid == 0) s_last = (atomicAdd(p.tickets + tile, 1u) == (unsigned)p.splits - 1u);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int c = n0 + wn + 8 * j + 2 * t;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = m0 + wm + g + 8 * h;
+            if (r >= p.M) continue;
+            float v0 = 0.f, v1 = 0.f;
+            for (int s = 0; s < p.splits; ++s) {
+                const float* src = p.partial + ((int64_t)s * p.M + r) * p.N + c;
+                if (c < p.N) v0 += __ldcg(src);
+                if (c + 1 < p.N) v1 += __ldcg(src + 1);
+            }
+            finish(r, c, v0, v1);
+        }
+    }
+    if (tid == 0) p.tickets[tile] = 0u;
+}
+
+// column sums of a (masked) [rows, cols] matrix: bias gradients
+__global__ void __launch_bounds__(256)
+colsum_masked_kernel(const float* __restrict__ X, const float* __restrict__ mask, int rows, int cols, float* __restrict__ out) {
+    __shared__ float red[8][32 + 1];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ry = threadIdx.x >> 5;
+    float s = 0.f;
+    if (c < cols)
+        for (int r = ry; r < rows; r += 8) {
+            const float v = X[(int64_t)r * cols + c];
+            s += (mask == nullptr || mask[(int64_t)r * cols + c] > 0.f) ? v : 0.f;
+        }
+    red[ry][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (ry == 0 && c < cols) {
+        float tot = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot += red[i][threadIdx.x];
+        out[c] = tot;
+    }
+}
+
+int operand_mode(const float* p, const float* mask, int64_t rs, int64_t cs, int rows, int K) {
+    const bool al = aligned16(p) && (mask == nullptr || aligned16(mask));
+    if (cs == 1 && al && rs % 4 == 0 && K % 4 == 0) return kVecK;
+    if (rs == 1 && al && cs % 4 == 0 && rows % 4 == 0) return kVecR;
+    return kScalar;
+}
+
+}  // namespace
+
+int gemm_splits(int M, int N, int K) {
+    const int tiles = ((M + kTM - 1) / kTM) * ((N + kTN - 1) / kTN);
+    const int ktiles = (K + kTK - 1) / kTK;
+    if (tiles * 5 >= sm_count() * 4) return 1;                 // >= 0.8 wave already
+    int s = (sm_count() + tiles - 1) / tiles;
+    s = s < ktiles / 4 ? s : ktiles / 4;                       // >= 4 K-slabs per split: the fix-up costs two L2 round trips
+    s = s < kMaxSplits ? s : kMaxSplits;
+    return s < 1 ? 1 : s;
+}
+
+size_t gemm_workspace_bytes(int M, int N, int K) {
+    const int s = gemm_splits(M, N, K);
+    if (s == 1) return 0;
+    const size_t tiles = (size_t)((M + kTM - 1) / kTM) * ((N + kTN - 1) / kTN);
+    return ((tiles * sizeof(unsigned) + 255) / 256) * 256 + (size_t)s * M * N * sizeof(float);
+}
+
+// workspace == nullptr forces a single split (no workspace needed).  The first `tiles` words of the workspace are the
+// ticket counters: they must be zero before the first use and are left zero by every launch.
+int gemm_nt(const float* A, const float* a_mask, int64_t a_rs, int64_t a_cs, const float* Bm, int64_t b_rs, int64_t b_cs,
+            const float* bias, float* C, int64_t ldc, int M, int N, int K, int relu, void* workspace, size_t workspace_bytes,
+            cudaStream_t st) {
+    GemmParams p;
+    p.a = Operand{A, a_rs, a_cs, M, operand_mode(A, a_mask, a_rs, a_cs, M, K)};
+    p.b = Operand{Bm, b_rs, b_cs, N, operand_mode(Bm, nullptr, b_rs, b_cs, N, K)};
+    p.a_mask = a_mask; p.bias = bias; p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.relu = relu;
+    p.splits = 1; p.partial = nullptr; p.tickets = nullptr;
+    if (workspace != nullptr) {
+        const int s = gemm_splits(M, N, K);
+        if (s > 1) {
+            MOMA_REQUIRE(workspace_bytes >= gemm_workspace_bytes(M, N, K) && aligned16(workspace), MOMA_ERR_WORKSPACE,
+                         "gemm: workspace too small or unaligned");
+            const size_t tiles = (size_t)((M + kTM - 1) / kTM) * ((N + kTN - 1) / kTN);
+            p.splits = s;
+            p.tickets = static_cast<unsigned int*>(workspace);
+            p.partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + ((tiles * sizeof(unsigned) + 255) / 256) * 256);
+        }
+    }
+    const dim3 grid((N + kTN - 1) / kTN, (M + kTM - 1) / kTM, p.splits);
+    if (a_mask) gemm3xtf32_kernel<true><<<grid, kThreads, 0, st>>>(p);
+    else gemm3xtf32_kernel<false><<<grid, kThreads, 0, st>>>(p);
+    MOMA_CUDA_LAUNCH_CHECK("gemm3xtf32");
+    return MOMA_OK;
+}
+
+void colsum_masked(const float* X, const float* mask, int rows, int cols, float* out, cudaStream_t st) {
+    colsum_masked_kernel<<<(cols + 31) / 32, 256, 0, st>>>(X, mask, rows, cols, out);
+}
+
+}  // namespace moma
+
+using namespace moma;
+
+// ----------------------------------------------------------------------------- C ABI: Linear (+ReLU)
+// Replaces the nn.Linear / nn.ReLU pairs of the projection heads (MoMA/criterion_moco_att.py:254-305).
+extern "C" __attribute__((visibility("default"))) size_t moma_linear_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+    if (M <= 0 || N <= 0 || K <= 0 || M > (1 << 24) || N > (1 << 24) || K > (1 << 24)) return 0;
+    // forward: [M,N] over K; backward: dX [M,K] over N and dW [N,K] over M run concurrently on disjoint halves
+    const size_t f = gemm_workspace_bytes((int)M, (int)N, (int)K);
+    const size_t b = gemm_workspace_bytes((int)M, (int)K, (int)N) + gemm_workspace_bytes((int)N, (int)K, (int)M);
+    return (f > b ? f : b) + 256;
+}
+
+extern "C" __attribute__((visibility("default"))) int moma_linear_fwd(
+    const float* x, const float* w, const float* b, int64_t M, int64_t N, int64_t K, int relu, float* y,
+    void* workspace, size_t workspace_bytes, moma_stream_t stream) {
+    MOMA_REQUIRE(x && w && y, MOMA_ERR_INVALID, "linear_fwd: null pointer");
+    MOMA_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1 << 24) && N < (1 << 24) && K < (1 << 24), MOMA_ERR_INVALID,
+                 "linear_fwd: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+    int rc = gemm_nt(x, nullptr, K, 1, w, K, 1, b, y, N, (int)M, (int)N, (int)K, relu, workspace, workspace_bytes, as_stream(stream));
+    if (rc != MOMA_OK) return rc;
+    note_launches(1);
+    return MOMA_OK;
+}
+
+namespace {
+struct LinStreams { cudaStream_t s1 = nullptr; cudaEvent_t fork = nullptr, join = nullptr; bool ok = false; };
+LinStreams& lin_streams() {
+    static thread_local LinStreams b;
+    static thread_local bool init = false;
+    if (!init) {
+        init = true;
+        bool good = cudaStreamCreateWithFlags(&b.s1, cudaStreamNonBlocking) == cudaSuccess;
+        good = good && cudaEventCreateWithFlags(&b.fork, cudaEventDisableTiming) == cudaSuccess;
+        good = good && cudaEventCreateWithFlags(&b.join, cudaEventDisableTiming) == cudaSuccess;
+        b.ok = good;
+        if (!good) cudaGetLastError();
+    }
+    return b;
+}
+}  // namespace
+
+// y is the forward OUTPUT (post-ReLU when relu != 0; used as the ReLU mask, may be NULL when relu == 0).
+// Any of grad_x / grad_w / grad_b may be NULL.  dX runs on `stream`, dW / db on an internal side stream that is
+// forked from and joined back into `stream` (parallel branches under graph capture).
+extern "C" __attribute__((visibility("default"))) int moma_linear_bwd(
+    const float* x, const float* w, const float* y, const float* grad_y, int64_t M, int64_t N, int64_t K, int relu,
+    float* grad_x, float* grad_w, float* grad_b, void* workspace, size_t workspace_bytes, moma_stream_t stream) {
+    MOMA_REQUIRE(x && w && grad_y && (!relu || y), MOMA_ERR_INVALID, "linear_bwd: null pointer");
+    MOMA_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1 << 24) && N < (1 << 24) && K < (1 << 24), MOMA_ERR_INVALID,
+                 "linear_bwd: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+    cudaStream_t st = as_stream(stream);
+    const float* mask = relu ? y : nullptr;
+    const int m = (int)M, n = (int)N, k = (int)K;
+    char* ws = static_cast<char*>(workspace);
+    const size_t need_x = gemm_workspace_bytes(m, k, n), need_w = gemm_workspace_bytes(n, k, m);
+    const bool have_ws = ws != nullptr && workspace_bytes >= need_x + need_w + 256 && aligned16(ws);
+    void* ws_x = have_ws && need_x ? ws : nullptr;
+    void* ws_w = have_ws && need_w ? ws + ((need_x + 255) / 256) * 256 : nullptr;
+    LinStreams& ls = lin_streams();
+    const bool side = ls.ok && (grad_w || grad_b) && grad_x;
+    cudaStream_t s1 = side ? ls.s1 : st;
+    if (side) { cudaEventRecord(ls.fork, st); cudaStreamWaitEvent(s1, ls.fork, 0); }
+    int launches = 0, rc = MOMA_OK;
+    // dW[n, k] = sum_m g[m, n] x[m, k]
+    if (grad_w) {
+        rc = gemm_nt(grad_y, mask, 1, N, x, 1, K, nullptr, grad_w, K, n, k, m, 0, ws_w, need_w, s1);
+        if (rc != MOMA_OK) return rc;
+        ++launches;
+    }
+    if (grad_b) { colsum_masked(grad_y, mask, m, n, grad_b, s1); ++launches; }
+    // dX[m, k] = sum_n g[m, n] w[n, k]
+    if (grad_x) {
+        rc = gemm_nt(grad_y, mask, N, 1, w, 1, K, nullptr, grad_x, K, m, k, n, 0, ws_x, need_x, st);
+        if (rc != MOMA_OK) return rc;
+        ++launches;
+    }
+    if (side) { cudaEventRecord(ls.join, s1); cudaStreamWaitEvent(st, ls.join, 0); }
+    MOMA_CUDA_LAUNCH_CHECK("linear_bwd");
+    note_launches(launches);
+    return MOMA_OK;
+}

@@ -445,3 +445,60 @@ def attention_rows(x, w_qkv, b_qkv, w_proj, b_proj, num_heads: int, q_start: int
 
 def attention_supported(C: int, H: int) -> bool:
     return C % H == 0 and (C // H) in (8, 16, 32, 64, 128)
+
+
+# -------------------------------------------------------------------------- projection-head Linear (+ReLU)
+_LINEAR_WS = {}
+
+
+def _linear_workspace(key, nbytes: int, device):
+    """Zeroed split-K workspace of one call site (a layer's forward or backward).  The kernels leave the ticket
+    counters zero, so it is zeroed exactly once; a call site never runs concurrently with itself."""
+    ws = _LINEAR_WS.get(key)
+    if ws is None or ws.numel() < nbytes or ws.device != device:
+        ws = torch.zeros(max(nbytes, 16), dtype=torch.uint8, device=device)
+        _LINEAR_WS[key] = ws
+    return ws
+
+
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, relu, key):
+        lib = _lib.load()
+        xc, wc = _f32c(x), _f32c(w)
+        bc = _f32c(b) if b is not None else None
+        M, K = xc.shape
+        N = wc.shape[0]
+        y = torch.empty((M, N), dtype=torch.float32, device=xc.device)
+        nbytes = int(lib.moma_linear_workspace_bytes(M, N, K))
+        ws = _linear_workspace((key, "f", M, N, K), nbytes, xc.device)
+        check(lib.moma_linear_fwd(_p(xc), _p(wc), _p(bc), M, N, K, int(relu), _p(y), _p(ws), nbytes, _stream()))
+        ctx.save_for_backward(xc, wc, y if relu else None)
+        ctx.relu, ctx.key, ctx.has_b = bool(relu), key, b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        xc, wc, y = ctx.saved_tensors
+        M, K = xc.shape
+        N = wc.shape[0]
+        gy = _f32c(gy)
+        need = ctx.needs_input_grad
+        gx = torch.empty_like(xc) if need[0] else None
+        gw = torch.empty_like(wc) if need[1] else None
+        gb = torch.empty(N, dtype=torch.float32, device=xc.device) if (need[2] and ctx.has_b) else None
+        nbytes = int(lib.moma_linear_workspace_bytes(M, N, K))
+        ws = _linear_workspace((ctx.key, "b", M, N, K), nbytes, xc.device)
+        check(lib.moma_linear_bwd(_p(xc), _p(wc), _p(y), _p(gy), M, N, K, int(ctx.relu), _p(gx), _p(gw), _p(gb),
+                                  _p(ws), nbytes, _stream()))
+        return gx, gw, gb, None, None
+
+
+def linear(x, weight, bias=None, relu: bool = False, key=None):
+    """nn.Linear (+ nn.ReLU) of the projection heads (criterion_moco_att.py:254-305) on x [M, K]:
+    3xTF32 tensor-core GEMM with the bias / ReLU epilogue fused; autograd through the same kernels."""
+    _need_cuda(x, weight)
+    if x.dim() != 2 or weight.dim() != 2 or x.shape[1] != weight.shape[1]:
+        raise RuntimeError(f"moma_b200.linear: bad shapes x {tuple(x.shape)} weight {tuple(weight.shape)}")
+    return _Linear.apply(x, weight, bias, bool(relu), key if key is not None else id(weight))

@@ -551,3 +551,66 @@ def test_attention_row_subset_and_strided_enqueue(ops):
         start = (rank - index) % W
         ops.enqueue(cu(keys[start::W].copy()), shard, None, K, index, rank=rank, world=W, key_start=start, key_stride=W)
         assert np.array_equal(npy(shard), want[rank::W])
+
+
+# ----------------------------------------------------------------------------- projection-head Linear (3xTF32 GEMM)
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K,relu,bias", [
+    (256, 512, 512, True, True),      # embed_s layer 1 (C2)
+    (256, 128, 512, False, True),     # embed_s layer 2: split-K
+    (64, 128, 2048, False, True),     # long K, many splits
+    (7, 33, 19, True, True),          # ragged: scalar copies, partial tiles
+    (1, 128, 512, False, False),      # one row (B == 1), no bias
+    (130, 36, 100, True, False),      # K % 32 != 0, M % 32 != 0
+])
+def test_linear_matches_fp64_reference(M, N, K, relu, bias):
+    """moma_linear_fwd / moma_linear_bwd against torch in float64 (the reference's nn.Linear + nn.ReLU,
+    criterion_moco_att.py:254-305).  Tolerance 2e-6 relative: the 3xTF32 product keeps fp32-level accuracy."""
+    import torch
+    from moma_b200 import ops
+    dev = torch.device("cuda")
+    torch.manual_seed(M * 7 + N * 3 + K)
+    x = torch.randn(M, K, device=dev, requires_grad=True)
+    w = (torch.randn(N, K, device=dev) / K ** 0.5).requires_grad_()
+    b = torch.randn(N, device=dev, requires_grad=True) if bias else None
+    gy = torch.randn(M, N, device=dev)
+    for rep in range(2):                                   # twice: the split-K ticket counters must reset themselves
+        y = ops.linear(x, w, b, relu=relu)
+        grads = torch.autograd.grad(y, (x, w) + ((b,) if bias else ()), gy)
+    xd, wd = x.detach().double().requires_grad_(), w.detach().double().requires_grad_()
+    bd = b.detach().double().requires_grad_() if bias else None
+    yd = torch.nn.functional.linear(xd, wd, bd)
+    if relu:
+        # same ReLU mask as the kernel's own output (an element within rounding of 0 may legitimately differ)
+        yd = yd * (y.detach() > 0).double()
+    gd = torch.autograd.grad(yd, (xd, wd) + ((bd,) if bias else ()), gy.double())
+
+    def rel(a, ref):
+        return float((a.double() - ref).norm() / ref.norm().clamp_min(1e-30))
+    assert rel(y.detach(), yd.detach()) < 2e-6
+    for got, want in zip(grads, gd):
+        assert rel(got, want) < 2e-6
+
+
+@pytest.mark.gpu
+def test_linear_is_deterministic_and_head_uses_it():
+    """Split-K reduces in split order: bit-identical results run to run; the `mlp` head routes its Linears here."""
+    import torch
+    from argparse import Namespace
+    from moma_b200 import CMO, _lib
+    dev = torch.device("cuda")
+    torch.manual_seed(5)
+    crit = CMO(Namespace(head="mlp", attn="self", s_dim=512, t_dim=2048, feat_dim=128)).to(dev)
+    x = torch.randn(64, 512, device=dev, requires_grad=True)
+    lib = _lib.load()
+    lib.moma_debug_launch_count(1)
+    y1 = crit.embed_s(x)
+    g1 = torch.autograd.grad(y1.square().sum() + y1[:, 0].sum(), x)[0]
+    n = int(lib.moma_debug_launch_count(0))
+    assert n >= 7          # 2 linear fwd + l2norm fwd, l2norm bwd, 2 x (dX, dW, db) backward launches
+    y2 = crit.embed_s(x)
+    g2 = torch.autograd.grad(y2.square().sum() + y2[:, 0].sum(), x)[0]
+    assert torch.equal(y1, y2) and torch.equal(g1, g2)
+    ref = torch.nn.Sequential(*list(crit.embed_s))        # plain torch modules over the same parameters
+    yr = ref(x.detach())
+    assert float((y1 - yr).norm() / yr.norm()) < 2e-6
