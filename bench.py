@@ -179,9 +179,7 @@ class CriterionStep:
         if not hasattr(self, "_side"):
             self._side = [torch.cuda.Stream(self.dev) for _ in range(3)]
         s_ema, s_t, s_u = self._side
-        s_ema.wait_stream(main); s_t.wait_stream(main)
-        with torch.cuda.stream(s_ema):
-            self.trainer.momentum_update(self.student, self.teacher, opt.alpha)
+        s_t.wait_stream(main)
         with torch.cuda.stream(s_t):
             if self.head_ema:
                 self.trainer.momentum_update(crit.embed_s, crit.embed_t, opt.alpha)
@@ -197,6 +195,11 @@ class CriterionStep:
                     all_k = crit.atts_queue(all_k)
             k = crit.atts_k(k0)
         f_s = crit.embed_s(self.feat_s)
+        # The backbone EMA (bandwidth-bound, 270 MB of traffic) is forked AFTER the projection heads: they are the only
+        # other kernels of the step that miss in L2 (cold weights), everything after them is latency-bound and L2-resident.
+        s_ema.wait_stream(main)
+        with torch.cuda.stream(s_ema):
+            self.trainer.momentum_update(self.student, self.teacher, opt.alpha)
         f_s = crit.atts_q(f_s)
         main.wait_stream(s_t); main.wait_stream(s_u)
         loss = self._loss_and_backward(f_s, k, all_k, self.feat_s, owned_k=owned)

@@ -18,6 +18,10 @@ int fail(int code, const char* fmt, ...) {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
     return code;
 }
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("MOMA_B200_PDL"); return !(e != nullptr && e[0] == '0'); }();
+    return on;
+}
 bool use_simt_gemm() {
     static const bool simt = [] { const char* e = getenv("MOMA_B200_GEMM"); return e != nullptr && std::string(e) == "simt"; }();
     return simt;

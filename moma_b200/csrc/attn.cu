@@ -125,6 +125,8 @@ static void sgemm(const float* A, int64_t a_rs, int64_t a_cs, const float* Bm, i
 // column sums: out[c] = sum_r X[r, c]   (bias gradients)
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ X, int rows, int cols, float* __restrict__ out) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ float red[8][32 + 1];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     const int ry = threadIdx.x >> 5;
@@ -170,6 +172,18 @@ __device__ __forceinline__ void load_rows(float* dst, const float* __restrict__ 
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
         if (row0 + r < N) a = *reinterpret_cast<const float4*>(src + (int64_t)(row0 + r) * ldg + 4 * v);
         *reinterpret_cast<float4*>(dst + r * LD + 4 * v) = a;
+    }
+}
+
+// same, asynchronously (cp.async, zero-filled past row N): the caller commits / waits the group
+template <int HD>
+__device__ __forceinline__ void load_rows_async(float* dst, const float* __restrict__ src, int64_t ldg,
+                                                int row0, int rows, int N) {
+    constexpr int NV = HD / 4, LD = HD + 4;
+    for (int i = threadIdx.x; i < rows * NV; i += kAThreads) {
+        const int r = i / NV, v = i - r * NV;
+        const bool ok = row0 + r < N;
+        cp_async16(dst + r * LD + 4 * v, ok ? src + (int64_t)(row0 + r) * ldg + 4 * v : src, ok);
     }
 }
 
@@ -227,6 +241,8 @@ template <int HD, int RW>
 __global__ void __launch_bounds__(kAThreads)
 attn_fwd_kernel(const float* __restrict__ qkv, int N, int C, float scale, float* __restrict__ o,
                 float* __restrict__ lse, int q_start, int q_stride, int NQ) {
+    pdl_wait();
+    pdl_launch_dependents();
     // queries are the NQ rows q_start + i * q_stride of the N tokens (all rows by default); o / lse are
     // indexed by the compact query index i
     using Cfg = AttnCfg<HD, RW>;
@@ -248,9 +264,8 @@ attn_fwd_kernel(const float* __restrict__ qkv, int N, int C, float scale, float*
         constexpr int NV = HD / 4;
         for (int i = threadIdx.x; i < kAR * NV; i += kAThreads) {
             const int r = i / NV, v = i - r * NV;
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (i0 + r < NQ) a = *reinterpret_cast<const float4*>(qg + (int64_t)(q_start + (i0 + r) * q_stride) * ldg + 4 * v);
-            *reinterpret_cast<float4*>(q_s + r * Cfg::LD + 4 * v) = a;
+            const bool ok = i0 + r < NQ;
+            cp_async16(q_s + r * Cfg::LD + 4 * v, ok ? qg + (int64_t)(q_start + (i0 + r) * q_stride) * ldg + 4 * v : qg, ok);
         }
     }
     float m_run[RW], l_run[RW];
@@ -261,8 +276,13 @@ attn_fwd_kernel(const float* __restrict__ qkv, int N, int C, float scale, float*
 
     for (int j0 = 0; j0 < N; j0 += KT) {
         if (j0 > 0) __syncthreads();
-        load_rows<HD>(k_s, kg, ldg, j0, KT, N);
-        load_rows<HD>(v_s, vg, ldg, j0, KT, N);
+        // K (with Q on the first tile) and V arrive as two cp.async groups: the scores start as soon as K is in,
+        // the V tile lands while they and the softmax are computed
+        load_rows_async<HD>(k_s, kg, ldg, j0, KT, N);
+        cp_async_commit();
+        load_rows_async<HD>(v_s, vg, ldg, j0, KT, N);
+        cp_async_commit();
+        cp_async_wait<1>();
         __syncthreads();
         float s[RW][CC];
         dot_tile<HD, KT, RW>(q_s, k_s, warp, lane, s);
@@ -296,7 +316,8 @@ attn_fwd_kernel(const float* __restrict__ qkv, int N, int C, float scale, float*
 #pragma unroll
             for (int c = 0; c < Cfg::CPL; ++c) acc[r][c] *= cr;
         }
-        __syncwarp();
+        cp_async_wait<0>();
+        __syncthreads();
         acc_tile<HD, KT, RW>(p_s, v_s, warp, lane, acc);
     }
     const int cbase = Cfg::cbase(lane);
@@ -325,6 +346,8 @@ attn_fwd_kernel(const float* __restrict__ qkv, int N, int C, float scale, float*
 __global__ void __launch_bounds__(256)
 attn_probs_kernel(const float* __restrict__ qkv, const float* __restrict__ lse, int N, int C, int H,
                   float scale, float* __restrict__ probs) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int hd = C / H;
     const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (idx >= (int64_t)H * N * N) return;
@@ -343,6 +366,8 @@ attn_probs_kernel(const float* __restrict__ qkv, const float* __restrict__ lse, 
 __global__ void __launch_bounds__(128)
 attn_delta_kernel(const float* __restrict__ dO, const float* __restrict__ o, int N, int C, int H,
                   float* __restrict__ delta) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int w = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (w >= N * H) return;
     const int i = w / H, h = w - i * H, hd = C / H;
@@ -359,20 +384,27 @@ __global__ void __launch_bounds__(kAThreads)
 attn_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
                    const float* __restrict__ lse, const float* __restrict__ delta, int N, int C,
                    float scale, float* __restrict__ dqkv) {
+    pdl_wait();
+    pdl_launch_dependents();
     using Cfg = AttnCfg<HD, RW>;
     constexpr int kAR = Cfg::AR;
     constexpr int KT = Cfg::KT_BWD, CC = KT / 32, LDP = KT + 4;
     extern __shared__ __align__(16) float sm[];
     float* q_s = sm;                          // [32][LD]
     float* do_s = q_s + kAR * Cfg::LD;        // [32][LD]
-    float* k_s = do_s + kAR * Cfg::LD;        // [KT][LD]
-    float* v_s = k_s + KT * Cfg::LD;          // [KT][LD]
-    float* p_s = v_s + KT * Cfg::LD;          // [32][LDP]  (holds dS)
+    float* kv_s = do_s + kAR * Cfg::LD;       // 2 x { [KT][LD] keys, [KT][LD] values }: double-buffered column tiles
+    float* p_s = kv_s + 4 * KT * Cfg::LD;     // [32][LDP]  (holds dS)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int h = blockIdx.y, i0 = blockIdx.x * kAR;
     const int64_t ldg = 3 * (int64_t)C;
-    load_rows<HD>(q_s, qkv + h * HD, ldg, i0, kAR, N);
-    load_rows<HD>(do_s, dO + h * HD, C, i0, kAR, N);
+    auto issue_kv = [&](int buf, int j0) {
+        load_rows_async<HD>(kv_s + (2 * buf) * KT * Cfg::LD, qkv + C + h * HD, ldg, j0, KT, N);
+        load_rows_async<HD>(kv_s + (2 * buf + 1) * KT * Cfg::LD, qkv + 2 * C + h * HD, ldg, j0, KT, N);
+        cp_async_commit();
+    };
+    load_rows_async<HD>(q_s, qkv + h * HD, ldg, i0, kAR, N);
+    load_rows_async<HD>(do_s, dO + h * HD, C, i0, kAR, N);
+    issue_kv(0, 0);
     float lse_r[RW], del_r[RW];
 #pragma unroll
     for (int r = 0; r < RW; ++r) {
@@ -381,11 +413,12 @@ attn_bwd_dq_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
         del_r[r] = row < N ? delta[(int64_t)h * N + row] : 0.f;
     }
     float acc[Cfg::RPL][Cfg::CPL] = {};
-    for (int j0 = 0; j0 < N; j0 += KT) {
-        if (j0 > 0) __syncthreads();
-        load_rows<HD>(k_s, qkv + C + h * HD, ldg, j0, KT, N);
-        load_rows<HD>(v_s, qkv + 2 * C + h * HD, ldg, j0, KT, N);
-        __syncthreads();
+    for (int j0 = 0, it = 0; j0 < N; j0 += KT, ++it) {
+        cp_async_wait<0>();
+        __syncthreads();                      // tile `it` has landed; everyone is done with the other buffer
+        if (j0 + KT < N) issue_kv((it + 1) & 1, j0 + KT);       // next tile in flight during this one's math
+        const float* k_s = kv_s + (2 * (it & 1)) * KT * Cfg::LD;
+        const float* v_s = k_s + KT * Cfg::LD;
         float s[RW][CC], dp[RW][CC];
         dot_tile<HD, KT, RW>(q_s, k_s, warp, lane, s);
         dot_tile<HD, KT, RW>(do_s, v_s, warp, lane, dp);
@@ -419,38 +452,46 @@ __global__ void __launch_bounds__(kAThreads)
 attn_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
                     const float* __restrict__ lse, const float* __restrict__ delta, int N, int C,
                     float scale, float* __restrict__ dqkv) {
+    pdl_wait();
+    pdl_launch_dependents();
     using Cfg = AttnCfg<HD, RW>;
     constexpr int kAR = Cfg::AR;
     constexpr int KT = Cfg::KT_BWD, CC = KT / 32, LDP = KT + 4;
     extern __shared__ __align__(16) float sm[];
     float* k_s = sm;                           // [32][LD]  own keys
     float* v_s = k_s + kAR * Cfg::LD;          // [32][LD]  own values
-    float* q_s = v_s + kAR * Cfg::LD;          // [KT][LD]  query tile
-    float* do_s = q_s + KT * Cfg::LD;          // [KT][LD]  dO tile
-    float* p_s = do_s + KT * Cfg::LD;          // [32][LDP]  P^T
+    float* qd_s = v_s + kAR * Cfg::LD;         // 2 x { [KT][LD] query tile, [KT][LD] dO tile }: double-buffered
+    float* p_s = qd_s + 4 * KT * Cfg::LD;      // [32][LDP]  P^T
     float* ds_s = p_s + kAR * LDP;             // [32][LDP]  dS^T
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int h = blockIdx.y, j0 = blockIdx.x * kAR;
     const int64_t ldg = 3 * (int64_t)C;
-    load_rows<HD>(k_s, qkv + C + h * HD, ldg, j0, kAR, N);
-    load_rows<HD>(v_s, qkv + 2 * C + h * HD, ldg, j0, kAR, N);
+    auto issue_qd = [&](int buf, int i0) {
+        load_rows_async<HD>(qd_s + (2 * buf) * KT * Cfg::LD, qkv + h * HD, ldg, i0, KT, N);
+        load_rows_async<HD>(qd_s + (2 * buf + 1) * KT * Cfg::LD, dO + h * HD, C, i0, KT, N);
+        cp_async_commit();
+    };
+    load_rows_async<HD>(k_s, qkv + C + h * HD, ldg, j0, kAR, N);
+    load_rows_async<HD>(v_s, qkv + 2 * C + h * HD, ldg, j0, kAR, N);
+    issue_qd(0, 0);
     float acc_k[Cfg::RPL][Cfg::CPL] = {};
     float acc_v[Cfg::RPL][Cfg::CPL] = {};
-    for (int i0 = 0; i0 < N; i0 += KT) {
-        if (i0 > 0) __syncthreads();
-        load_rows<HD>(q_s, qkv + h * HD, ldg, i0, KT, N);
-        load_rows<HD>(do_s, dO + h * HD, C, i0, KT, N);
+    for (int i0 = 0, it = 0; i0 < N; i0 += KT, ++it) {
+        cp_async_wait<0>();
         __syncthreads();
-        float st[RW][CC], dpt[RW][CC];
-        dot_tile<HD, KT, RW>(k_s, q_s, warp, lane, st);      // st[r][cc] = k_j . q_i
-        dot_tile<HD, KT, RW>(v_s, do_s, warp, lane, dpt);    // dpt      = v_j . do_i
-        float lse_c[CC], del_c[CC];
+        if (i0 + KT < N) issue_qd((it + 1) & 1, i0 + KT);
+        const float* q_s = qd_s + (2 * (it & 1)) * KT * Cfg::LD;
+        const float* do_s = q_s + KT * Cfg::LD;
+        float lse_c[CC], del_c[CC];                          // issued before the dot products: their latency hides there
 #pragma unroll
         for (int cc = 0; cc < CC; ++cc) {
             const int i = i0 + lane + 32 * cc;
             lse_c[cc] = i < N ? lse[(int64_t)h * N + i] : 0.f;
             del_c[cc] = i < N ? delta[(int64_t)h * N + i] : 0.f;
         }
+        float st[RW][CC], dpt[RW][CC];
+        dot_tile<HD, KT, RW>(k_s, q_s, warp, lane, st);      // st[r][cc] = k_j . q_i
+        dot_tile<HD, KT, RW>(v_s, do_s, warp, lane, dpt);    // dpt      = v_j . do_i
 #pragma unroll
         for (int r = 0; r < RW; ++r) {
             const bool rok = (j0 + warp * RW + r < N);
@@ -486,11 +527,11 @@ template <int HD, int RW> static size_t fwd_smem() {
 }
 template <int HD, int RW> static size_t dq_smem() {
     constexpr int KT = AttnCfg<HD, RW>::KT_BWD, AR = 4 * RW;
-    return (size_t)((2 * AR + 2 * KT) * (HD + 4) + AR * (KT + 4)) * sizeof(float);
+    return (size_t)((2 * AR + 4 * KT) * (HD + 4) + AR * (KT + 4)) * sizeof(float);
 }
 template <int HD, int RW> static size_t dkv_smem() {
     constexpr int KT = AttnCfg<HD, RW>::KT_BWD, AR = 4 * RW;
-    return (size_t)((2 * AR + 2 * KT) * (HD + 4) + 2 * AR * (KT + 4)) * sizeof(float);
+    return (size_t)((2 * AR + 4 * KT) * (HD + 4) + 2 * AR * (KT + 4)) * sizeof(float);
 }
 
 template <int HD, int RW>
@@ -499,8 +540,8 @@ static void launch_fwd_rw(const float* qkv, int N, int C, int H, float scale, fl
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(attn_fwd_kernel<HD, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<HD, RW>()); attr = true; }
     constexpr int AR = 4 * RW;
-    attn_fwd_kernel<HD, RW><<<dim3((NQ + AR - 1) / AR, H), kAThreads, fwd_smem<HD, RW>(), st>>>(qkv, N, C, scale, o, lse,
-                                                                                             q_start, q_stride, NQ);
+    launch_pdl(attn_fwd_kernel<HD, RW>, dim3((NQ + AR - 1) / AR, H), dim3(kAThreads), fwd_smem<HD, RW>(), st, qkv, N, C, scale, o, lse,
+               q_start, q_stride, NQ);
 }
 template <int HD, int RW>
 static void launch_bwd_rw(const float* qkv, const float* dO, const float* lse, const float* delta, int N, int C, int H,
@@ -514,11 +555,13 @@ static void launch_bwd_rw(const float* qkv, const float* dO, const float* lse, c
     constexpr int AR = 4 * RW;
     const dim3 grid((N + AR - 1) / AR, H);
     // dQ and dK/dV are independent: two streams (st2 was forked from st by the caller)
-    attn_bwd_dq_kernel<HD, RW><<<grid, kAThreads, dq_smem<HD, RW>(), st>>>(qkv, dO, lse, delta, N, C, scale, dqkv);
-    attn_bwd_dkv_kernel<HD, RW><<<grid, kAThreads, dkv_smem<HD, RW>(), st2>>>(qkv, dO, lse, delta, N, C, scale, dqkv);
+    launch_pdl(attn_bwd_dq_kernel<HD, RW>, grid, dim3(kAThreads), dq_smem<HD, RW>(), st, qkv, dO, lse, delta, N, C, scale, dqkv);
+    launch_pdl(attn_bwd_dkv_kernel<HD, RW>, grid, dim3(kAThreads), dkv_smem<HD, RW>(), st2, qkv, dO, lse, delta, N, C, scale, dqkv);
 }
 
-// rows per warp: the largest of {8, 4, 2} (but RW * HD >= 32) that still gives about one CTA per SM
+// rows per warp: the largest of {8, 4, 2} (but RW * HD >= 32) that still gives about one CTA per SM.  (One row per
+// warp -- two CTAs per SM -- was measured: each warp still reads the whole key tile from shared memory, so the
+// instruction count per SM rises as fast as the occupancy and the kernels do not get faster.)
 template <int HD> static int pick_rw(int N, int H) {
     constexpr int rw_min = HD >= 16 ? 2 : 4;
     const int target = sm_count() * 3 / 4;
@@ -604,7 +647,7 @@ extern "C" __attribute__((visibility("default"))) int moma_attn_fwd(const float*
     }
     if (attn_probs) {
         const int64_t tot = (int64_t)H * N * N;
-        attn_probs_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(qkv, lse, n, c, H, scale, attn_probs);
+        launch_pdl(attn_probs_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, qkv, lse, n, c, H, scale, attn_probs);
     }
     sgemm(o, C, 1, w_proj, C, 1, b_proj, y, C, n, c, c, st);
     MOMA_CUDA_LAUNCH_CHECK("attn_fwd");
@@ -674,10 +717,10 @@ extern "C" __attribute__((visibility("default"))) int moma_attn_bwd(const float*
     cudaStream_t s1 = bs.ok ? bs.s1 : st, s2 = bs.ok ? bs.s2 : st;
     if (bs.ok) { cudaEventRecord(bs.fork, st); cudaStreamWaitEvent(s1, bs.fork, 0); }
     // proj backward: dW_proj[co, ci] = sum_n dy[n, co] o[n, ci];  db = colsum(dy);  dO = dy W_proj
+    if (grad_b_proj) launch_pdl(colsum_kernel, dim3((c + 31) / 32), dim3(256), 0, s1, grad_y, n, c, grad_b_proj);
     if (grad_w_proj) sgemm(grad_y, 1, C, o, 1, C, nullptr, grad_w_proj, C, c, c, n, s1);
-    if (grad_b_proj) colsum_kernel<<<(c + 31) / 32, 256, 0, s1>>>(grad_y, n, c, grad_b_proj);
     sgemm(grad_y, C, 1, w_proj, 1, C, nullptr, dO, C, n, c, c, st);
-    attn_delta_kernel<<<(n * H + 3) / 4, 128, 0, st>>>(dO, o, n, c, H, delta);
+    launch_pdl(attn_delta_kernel, dim3((n * H + 3) / 4), dim3(128), 0, st, dO, o, n, c, H, delta);
     if (bs.ok) { cudaEventRecord(bs.d_o, st); cudaStreamWaitEvent(s2, bs.d_o, 0); }
     switch (hd) {
         case 8: launch_bwd<8>(qkv, dO, lse, delta, n, c, H, scale, dqkv, st, s2); break;
@@ -691,8 +734,8 @@ extern "C" __attribute__((visibility("default"))) int moma_attn_bwd(const float*
         cudaEventRecord(bs.dkv, s2); cudaStreamWaitEvent(st, bs.dkv, 0);    // st too
     }
     // qkv backward: dW_qkv[j, ci] = sum_n dqkv[n, j] x[n, ci]; db = colsum(dqkv); dx = dqkv W_qkv
+    if (grad_b_qkv) launch_pdl(colsum_kernel, dim3((3 * c + 31) / 32), dim3(256), 0, s2, dqkv, n, 3 * c, grad_b_qkv);
     if (grad_w_qkv) sgemm(dqkv, 1, 3 * C, x, 1, C, nullptr, grad_w_qkv, C, 3 * c, c, n, s2);
-    if (grad_b_qkv) colsum_kernel<<<(3 * c + 31) / 32, 256, 0, s2>>>(dqkv, n, 3 * c, grad_b_qkv);
     if (grad_x) sgemm(dqkv, 3 * C, 1, w_qkv, 1, C, nullptr, grad_x, C, n, c, 3 * c, st);
     if (bs.ok) {                                                             // join
         cudaEventRecord(bs.join1, s1); cudaStreamWaitEvent(st, bs.join1, 0);

@@ -14,6 +14,8 @@ template <bool kBackward>
 __global__ void __launch_bounds__(kNormWarps * 32)
 l2norm_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ out,
               int64_t rows, int64_t D, float eps) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * kNormWarps + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -75,6 +77,8 @@ enqueue_kernel(const float* __restrict__ keys, int64_t n, int64_t D, float* __re
                __nv_bfloat16* __restrict__ shadow, int64_t K, int64_t index,
                const int64_t* __restrict__ index_dev, int rank, int world, int normalize, float eps,
                int64_t key_start, int64_t key_stride) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int lane = threadIdx.x & 31;
     const int64_t j = (int64_t)blockIdx.x * kEnqWarps + (threadIdx.x >> 5);
     if (j >= n) return;
@@ -106,18 +110,24 @@ enqueue_kernel(const float* __restrict__ keys, int64_t n, int64_t D, float* __re
 
 __global__ void enqueue_ids_kernel(int64_t n, int64_t index, const int64_t* __restrict__ index_dev,
                                    int64_t K, int64_t* __restrict__ out) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (index_dev) index = *index_dev;
     if (j < n) out[j] = (j + index) % K;
 }
 
 __global__ void pointer_advance_kernel(int64_t* index_dev, int64_t n, int64_t K) {
+    pdl_wait();
+    pdl_launch_dependents();
     if (threadIdx.x == 0 && blockIdx.x == 0) *index_dev = (*index_dev + n) % K;
 }
 
 __global__ void __launch_bounds__(256)
 cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t nvec,
                  int64_t numel) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const float4* s4 = reinterpret_cast<const float4*>(src);
@@ -147,7 +157,7 @@ extern "C" __attribute__((visibility("default"))) int moma_l2norm_fwd(const floa
     int rc = check_rows("l2norm_fwd", x, y, rows, D);
     if (rc != MOMA_OK || rows == 0) return rc;
     const unsigned grid = (unsigned)((rows + kNormWarps - 1) / kNormWarps);
-    l2norm_kernel<false><<<grid, kNormWarps * 32, 0, as_stream(stream)>>>(x, nullptr, y, rows, D, eps);
+    launch_pdl(l2norm_kernel<false>, dim3(grid), dim3(kNormWarps * 32), 0, as_stream(stream), x, nullptr, y, rows, D, eps);
     MOMA_CUDA_LAUNCH_CHECK("l2norm_fwd");
     note_launches(1);
     return MOMA_OK;
@@ -159,7 +169,7 @@ extern "C" __attribute__((visibility("default"))) int moma_l2norm_bwd(const floa
     if (rc != MOMA_OK || rows == 0) return rc;
     MOMA_REQUIRE(grad_y && aligned16(grad_y), MOMA_ERR_ALIGN, "l2norm_bwd: grad_y null/unaligned");
     const unsigned grid = (unsigned)((rows + kNormWarps - 1) / kNormWarps);
-    l2norm_kernel<true><<<grid, kNormWarps * 32, 0, as_stream(stream)>>>(x, grad_y, grad_x, rows, D, eps);
+    launch_pdl(l2norm_kernel<true>, dim3(grid), dim3(kNormWarps * 32), 0, as_stream(stream), x, grad_y, grad_x, rows, D, eps);
     MOMA_CUDA_LAUNCH_CHECK("l2norm_bwd");
     note_launches(1);
     return MOMA_OK;
@@ -183,9 +193,9 @@ static int enqueue_impl(const float* keys, int64_t n, int64_t D, float* queue_f3
                  "enqueue: bf16 shadow needs D %% 8 == 0 and 16-byte alignment");
     if (n == 0) return MOMA_OK;
     const unsigned grid = (unsigned)((n + kEnqWarps - 1) / kEnqWarps);
-    enqueue_kernel<<<grid, kEnqWarps * 32, 0, as_stream(stream)>>>(
-        keys, n, D, queue_f32, static_cast<__nv_bfloat16*>(queue_bf16), K, index, index_dev,
-        shard_rank, shard_world, normalize, eps, key_start, key_stride);
+    launch_pdl(enqueue_kernel, dim3(grid), dim3(kEnqWarps * 32), 0, as_stream(stream),
+               keys, n, D, queue_f32, static_cast<__nv_bfloat16*>(queue_bf16), K, index, index_dev,
+               shard_rank, shard_world, normalize, eps, key_start, key_stride);
     MOMA_CUDA_LAUNCH_CHECK("enqueue");
     note_launches(1);
     return MOMA_OK;
@@ -212,7 +222,7 @@ extern "C" __attribute__((visibility("default"))) int moma_enqueue_ids(int64_t n
                                 int64_t* out_ids, moma_stream_t stream) {
     MOMA_REQUIRE(n >= 0 && K > 0 && (n == 0 || out_ids), MOMA_ERR_INVALID, "enqueue_ids: bad arguments");
     if (n == 0) return MOMA_OK;
-    enqueue_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(n, index, index_dev, K, out_ids);
+    launch_pdl(enqueue_ids_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, as_stream(stream), n, index, index_dev, K, out_ids);
     MOMA_CUDA_LAUNCH_CHECK("enqueue_ids");
     note_launches(1);
     return MOMA_OK;
@@ -220,7 +230,7 @@ extern "C" __attribute__((visibility("default"))) int moma_enqueue_ids(int64_t n
 
 extern "C" __attribute__((visibility("default"))) int moma_pointer_advance(int64_t* index_dev, int64_t n, int64_t K, moma_stream_t stream) {
     MOMA_REQUIRE(index_dev && n >= 0 && K > 0, MOMA_ERR_INVALID, "pointer_advance: bad arguments");
-    pointer_advance_kernel<<<1, 32, 0, as_stream(stream)>>>(index_dev, n, K);
+    launch_pdl(pointer_advance_kernel, dim3(1), dim3(32), 0, as_stream(stream), index_dev, n, K);
     MOMA_CUDA_LAUNCH_CHECK("pointer_advance");
     note_launches(1);
     return MOMA_OK;
@@ -235,8 +245,8 @@ extern "C" __attribute__((visibility("default"))) int moma_cast_bf16(const float
     const int64_t cap = (int64_t)sm_count() * 16;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    cast_bf16_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
-        src, static_cast<__nv_bfloat16*>(dst_bf16), nvec, numel);
+    launch_pdl(cast_bf16_kernel, dim3((unsigned)blocks), dim3(256), 0, as_stream(stream),
+               src, static_cast<__nv_bfloat16*>(dst_bf16), nvec, numel);
     MOMA_CUDA_LAUNCH_CHECK("cast_bf16");
     note_launches(1);
     return MOMA_OK;

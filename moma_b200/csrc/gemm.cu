@@ -38,18 +38,6 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-__device__ __forceinline__ void cp_async16(float* dst, const float* src, bool valid) {
-    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(valid ? 16 : 0) : "memory");
-}
-__device__ __forceinline__ void cp_async4(float* dst, const float* src, bool valid) {
-    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(valid ? 4 : 0) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 // operand access pattern of a [rows, K] operand
 enum : int { kVecK = 0,    // k contiguous (cs == 1), 16-byte aligned rows: 16-byte copies along k, tile kept [row][k]
              kVecR = 1,    // row index contiguous (rs == 1): 16-byte copies along the rows, tile kept [k][row]
@@ -119,6 +107,7 @@ gemm3xtf32_kernel(const GemmParams p) {
     const int a_base = (wm + g) * a_sr + t * a_sk;
     const int b_base = (wn + g) * b_sr + t * b_sk;
 
+    pdl_wait();                     // operands may come from the kernel launched just before this one
     auto issue = [&](int stage, int kt) {
         issue_tile(sA[stage], p.a.p, p.a, m0, kt * kTK, p.K);
         issue_tile(sB[stage], p.b.p, p.b, n0, kt * kTK, p.K);
@@ -174,6 +163,7 @@ gemm3xtf32_kernel(const GemmParams p) {
             for (int e = 0; e < 4; ++e) acc[j][e] += (plh[j][e] + phl[j][e]) + phh[j][e];     // small terms first
     }
     cp_async_wait<0>();
+    pdl_launch_dependents();        // the successor may start launching while the epilogue (and split-K fix-up) runs
 
     // accumulator fragment: acc[j][0..1] -> row wm + g, cols wn + 8j + 2t (+1); acc[j][2..3] -> row + 8
     auto finish = [&](int r, int c, float v0, float v1) {
@@ -238,6 +228,8 @@ gemm3xtf32_kernel(const GemmParams p) {
 // column sums of a (masked) [rows, cols] matrix: bias gradients
 __global__ void __launch_bounds__(256)
 colsum_masked_kernel(const float* __restrict__ X, const float* __restrict__ mask, int rows, int cols, float* __restrict__ out) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ float red[8][32 + 1];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     const int ry = threadIdx.x >> 5;
@@ -270,7 +262,7 @@ int gemm_splits(int M, int N, int K) {
     const int tiles = ((M + kTM - 1) / kTM) * ((N + kTN - 1) / kTN);
     const int ktiles = (K + kTK - 1) / kTK;
     if (tiles * 5 >= sm_count() * 4) return 1;                 // >= 0.8 wave already
-    int s = (sm_count() + tiles - 1) / tiles;
+    int s = sm_count() / tiles;                                // not more CTAs than SMs: an SM with two of them doubles the makespan
     s = s < ktiles / 4 ? s : ktiles / 4;                       // >= 4 K-slabs per split: the fix-up costs two L2 round trips
     s = s < kMaxSplits ? s : kMaxSplits;
     return s < 1 ? 1 : s;
@@ -305,14 +297,14 @@ int gemm_nt(const float* A, const float* a_mask, int64_t a_rs, int64_t a_cs, con
         }
     }
     const dim3 grid((N + kTN - 1) / kTN, (M + kTM - 1) / kTM, p.splits);
-    if (a_mask) gemm3xtf32_kernel<true><<<grid, kThreads, 0, st>>>(p);
-    else gemm3xtf32_kernel<false><<<grid, kThreads, 0, st>>>(p);
+    if (a_mask) launch_pdl(gemm3xtf32_kernel<true>, grid, dim3(kThreads), 0, st, p);
+    else launch_pdl(gemm3xtf32_kernel<false>, grid, dim3(kThreads), 0, st, p);
     MOMA_CUDA_LAUNCH_CHECK("gemm3xtf32");
     return MOMA_OK;
 }
 
 void colsum_masked(const float* X, const float* mask, int rows, int cols, float* out, cudaStream_t st) {
-    colsum_masked_kernel<<<(cols + 31) / 32, 256, 0, st>>>(X, mask, rows, cols, out);
+    launch_pdl(colsum_masked_kernel, dim3((cols + 31) / 32), dim3(256), 0, st, X, mask, rows, cols, out);
 }
 
 }  // namespace moma
@@ -380,13 +372,14 @@ extern "C" __attribute__((visibility("default"))) int moma_linear_bwd(
     cudaStream_t s1 = side ? ls.s1 : st;
     if (side) { cudaEventRecord(ls.fork, st); cudaStreamWaitEvent(s1, ls.fork, 0); }
     int launches = 0, rc = MOMA_OK;
+    // side branch: the short bias-gradient kernel first, so the branch ends with the long GEMM
+    if (grad_b) { colsum_masked(grad_y, mask, m, n, grad_b, s1); ++launches; }
     // dW[n, k] = sum_m g[m, n] x[m, k]
     if (grad_w) {
         rc = gemm_nt(grad_y, mask, 1, N, x, 1, K, nullptr, grad_w, K, n, k, m, 0, ws_w, need_w, s1);
         if (rc != MOMA_OK) return rc;
         ++launches;
     }
-    if (grad_b) { colsum_masked(grad_y, mask, m, n, grad_b, s1); ++launches; }
     // dX[m, k] = sum_n g[m, n] w[n, k]
     if (grad_x) {
         rc = gemm_nt(grad_y, mask, N, 1, w, 1, K, nullptr, grad_x, K, m, k, n, 0, ws_x, need_x, st);

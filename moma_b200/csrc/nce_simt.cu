@@ -209,6 +209,8 @@ nce_reduce_kernel(const float* __restrict__ part_m, const float* __restrict__ pa
                   float* __restrict__ out_a /* loss_rows | out_m */, float* __restrict__ out_O /* dq | out_O */,
                   int32_t* __restrict__ pos_is_max, float* __restrict__ out_b /* max_logit | out_l */,
                   float* __restrict__ out_c /* - | out_mmax */) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ float red[4];
     __shared__ float s_w[kCombChunk];
     __shared__ __align__(16) float s_o[4][kCombMaxD];
@@ -316,6 +318,8 @@ nce_reduce_kernel(const float* __restrict__ part_m, const float* __restrict__ pa
 __global__ void __launch_bounds__(256)
 nce_finalize_kernel(const float* __restrict__ rows, const int32_t* __restrict__ pim, int B,
                     float* __restrict__ loss_mean, float* __restrict__ acc_pct) {
+    pdl_wait();
+    pdl_launch_dependents();
     __shared__ float r1[8], r2[8];
     float s = 0.f, c = 0.f;
     for (int i = threadIdx.x; i < B; i += 256) { s += rows[i]; c += (float)pim[i]; }
@@ -466,13 +470,13 @@ extern "C" __attribute__((visibility("default"))) int moma_nce_combine(const flo
     MOMA_REQUIRE(part_m && part_l && part_mmax && part_O && q_f32 && kpos_f32 && loss_rows && dq_unit && pos_is_max,
                  MOMA_ERR_INVALID, "nce_combine: null pointer");
     MOMA_REQUIRE(D % 4 == 0 && aligned16(part_O), MOMA_ERR_ALIGN, "nce_combine: D %% 4 != 0 or part_O unaligned");
-    nce_reduce_kernel<true><<<(unsigned)B, kCombThreads, 0, as_stream(stream)>>>(
+    launch_pdl(nce_reduce_kernel<true>, dim3((unsigned)B), dim3(kCombThreads), 0, as_stream(stream),
         part_m, part_l, part_mmax, part_O, n_parts, q_f32, kpos_f32, (int)B, (int)D, inv_T, round_bf16, dq_scale,
         B, 1, B * D, D, 1, D, loss_rows, dq_unit, pos_is_max, max_logit, nullptr);
     MOMA_CUDA_LAUNCH_CHECK("nce_combine");
     note_launches(1);
     if (loss_mean && acc_pct) {
-        nce_finalize_kernel<<<1, 256, 0, as_stream(stream)>>>(loss_rows, pos_is_max, (int)B, loss_mean, acc_pct);
+        launch_pdl(nce_finalize_kernel, dim3(1), dim3(256), 0, as_stream(stream), loss_rows, pos_is_max, (int)B, loss_mean, acc_pct);
         MOMA_CUDA_LAUNCH_CHECK("nce_finalize");
         note_launches(1);
     }
@@ -486,7 +490,7 @@ extern "C" __attribute__((visibility("default"))) int moma_nce_merge(
     MOMA_REQUIRE(part_m && part_l && part_mmax && part_O && out_m && out_l && out_mmax && out_O,
                  MOMA_ERR_INVALID, "nce_merge: null pointer");
     MOMA_REQUIRE(D % 4 == 0 && aligned16(part_O), MOMA_ERR_ALIGN, "nce_merge: D %% 4 != 0 or part_O unaligned");
-    nce_reduce_kernel<false><<<(unsigned)B, kCombThreads, 0, as_stream(stream)>>>(
+    launch_pdl(nce_reduce_kernel<false>, dim3((unsigned)B), dim3(kCombThreads), 0, as_stream(stream),
         part_m, part_l, part_mmax, part_O, n_parts, nullptr, nullptr, (int)B, (int)D, 1.f, 0, 1.f,
         B, 1, B * D, D, 1, D, out_m, out_O, nullptr, out_l, out_mmax);
     MOMA_CUDA_LAUNCH_CHECK("nce_merge");
@@ -503,7 +507,7 @@ extern "C" __attribute__((visibility("default"))) int moma_nce_merge_packed(
     MOMA_REQUIRE(part_m && part_l && part_mmax && part_O && packed, MOMA_ERR_INVALID, "nce_merge_packed: null pointer");
     MOMA_REQUIRE(D % 4 == 0 && aligned16(part_O) && aligned16(packed), MOMA_ERR_ALIGN, "nce_merge_packed: alignment");
     const int64_t P = D + 4;
-    nce_reduce_kernel<false><<<(unsigned)B, kCombThreads, 0, as_stream(stream)>>>(
+    launch_pdl(nce_reduce_kernel<false>, dim3((unsigned)B), dim3(kCombThreads), 0, as_stream(stream),
         part_m, part_l, part_mmax, part_O, n_parts, nullptr, nullptr, (int)B, (int)D, 1.f, 0, 1.f,
         B, 1, B * D, D, P, P, packed + D, packed, nullptr, packed + D + 1, packed + D + 2);
     MOMA_CUDA_LAUNCH_CHECK("nce_merge_packed");
@@ -520,13 +524,13 @@ extern "C" __attribute__((visibility("default"))) int moma_nce_combine_packed(
                  "nce_combine_packed: null pointer");
     MOMA_REQUIRE(D % 4 == 0 && aligned16(packed), MOMA_ERR_ALIGN, "nce_combine_packed: alignment");
     const int64_t P = D + 4;
-    nce_reduce_kernel<true><<<(unsigned)B, kCombThreads, 0, as_stream(stream)>>>(
+    launch_pdl(nce_reduce_kernel<true>, dim3((unsigned)B), dim3(kCombThreads), 0, as_stream(stream),
         packed + D, packed + D + 1, packed + D + 2, packed, n_parts, q_f32, kpos_f32, (int)B, (int)D, inv_T,
         round_bf16, dq_scale, B * P, P, B * P, P, 1, D, loss_rows, dq_unit, pos_is_max, max_logit, nullptr);
     MOMA_CUDA_LAUNCH_CHECK("nce_combine_packed");
     note_launches(1);
     if (loss_mean && acc_pct) {
-        nce_finalize_kernel<<<1, 256, 0, as_stream(stream)>>>(loss_rows, pos_is_max, (int)B, loss_mean, acc_pct);
+        launch_pdl(nce_finalize_kernel, dim3(1), dim3(256), 0, as_stream(stream), loss_rows, pos_is_max, (int)B, loss_mean, acc_pct);
         MOMA_CUDA_LAUNCH_CHECK("nce_finalize");
         note_launches(1);
     }

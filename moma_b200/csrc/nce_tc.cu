@@ -569,6 +569,7 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     const int row_base = mt * kBM;
 
     if (nt <= 0) {      // empty split: neutral partials
+        pdl_wait();
         if (warp >= 4 && warp < 8) {
             const int row = row_base + ((warp & 3) << 5) + lane;
             if (row < B) {
@@ -608,6 +609,8 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
     auto s_colf = [&](int b) { return tmem + (uint32_t)(b * 128); };
+    // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the tail of the preceding kernel
+    pdl_wait();
 
     if (warp == 0) {
         // ===================================================== TMA producer
@@ -789,6 +792,7 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         }
 #undef SM_STAMP
 
+        pdl_launch_dependents();     // the combine kernel may start launching; it still waits for this grid to finish
         // epilogue: O (TMEM) -> part_O (each half writes its D/2 columns), stats by half 0
         const float l_half = (l2a.x + l2a.y) + (l2b.x + l2b.y);
         if (half == 1) bars->lsum[rit] = l_half;
@@ -907,8 +911,8 @@ static int launch2(const void* q, const void* queue, int64_t B, int64_t K_local,
     const float scale_log2 = inv_T * 1.4426950408889634f;
     int ablate = 0;
     if (kAblateHooks) { const char* e = getenv("MOMA_TC_ABLATE"); ablate = e ? atoi(e) : 0; }
-    nce_tc2_kernel<D><<<grid, C::THREADS, C::SMEM_TOTAL, st>>>(mq, mk, (int)B, (long long)K_local, scale_log2, n_splits,
-                                                              pm, pl, pmm, pO, dbg, ablate);
+    launch_pdl(nce_tc2_kernel<D>, grid, dim3(C::THREADS), (size_t)C::SMEM_TOTAL, st, mq, mk, (int)B, (long long)K_local, scale_log2,
+               n_splits, pm, pl, pmm, pO, dbg, ablate);
     MOMA_CUDA_LAUNCH_CHECK("nce_partial(bf16/tcgen05 v2)");
     note_launches(1);
     return MOMA_OK;

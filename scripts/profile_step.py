@@ -36,18 +36,17 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
             flush.fill_(1)
         g.replay()
     torch.cuda.synchronize()
-evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
-evs.sort(key=lambda e: e.time_range.start)
-# last replay only
-n = len(evs) // 3
-last = evs[-n:]
-t0 = last[0].time_range.start
-busy = 0.0
-prev_end = t0
-print(f"{'start':>8s} {'dur':>7s} {'gap':>6s}  kernel")
+kin = [e for e in prof.profiler.kineto_results.events() if str(e.device_type()).endswith("CUDA") and e.duration_ns() > 0]
+kin.sort(key=lambda e: e.start_ns())
+n = len(kin) // 3
+last = kin[-n:]
+t0 = last[0].start_ns()
+streams = {}
+print(f"{'start':>8s} {'end':>8s} {'dur':>7s}  st  kernel")
+busy = 0.0; end_max = t0
 for e in last:
-    st, en = e.time_range.start - t0, e.time_range.end - t0
-    print(f"{st:8.1f} {en - st:7.1f} {e.time_range.start - prev_end:6.1f}  {e.name[:90]}")
-    busy += en - st
-    prev_end = max(prev_end, e.time_range.end)
-print(f"total span {prev_end - t0:.1f} us, sum of kernel durations {busy:.1f} us, kernels {len(last)}")
+    sid = streams.setdefault(e.device_resource_id(), len(streams))
+    st, du = (e.start_ns() - t0) / 1e3, e.duration_ns() / 1e3
+    print(f"{st:8.1f} {st + du:8.1f} {du:7.1f}  {sid:2d}  {'    ' * sid}{e.name()[:70]}")
+    busy += du; end_max = max(end_max, e.start_ns() + e.duration_ns())
+print(f"total span {(end_max - t0) / 1e3:.1f} us, sum of kernel durations {busy:.1f} us, kernels {len(last)}")
