@@ -213,6 +213,32 @@ int moma_linear_bwd(const float *x, const float *w, const float *y, const float 
                     void *workspace, size_t workspace_bytes, moma_stream_t stream);
 
 /* ------------------------------------------------------------------------- *
+ * Peer-memory exchange for the K-sharded queue (one process per GPU, one node).
+ * Replaces, on the critical path of a step, the library collectives of
+ * learning/contrast_trainer.py:83-88 (_global_gather of the keys) and the query
+ * all-gather / partial-record all-to-all of the sharded InfoNCE pass: ONE kernel
+ * pushes this rank's rows into every peer's buffer over NVLink (remote stores
+ * of 8-byte (payload word, epoch tag) pairs: the flag travels in band, no fence
+ * or signal round trip), polls the peers' pairs and writes the payload to `out`.
+ * All ranks must issue the same sequence of calls per channel.
+ *   peer_bases_dev: device array [world] with the base address of every rank's
+ *     copy of one symmetric allocation (same size / layout on all ranks), zeroed
+ *     once, holding a control block of moma_peer_ctrl_bytes() bytes at ctrl_off
+ *     and, from data_off, 2 regions of region_bytes per channel (4 channels),
+ *     region_bytes >= 2 * world * bytes_per_rank.
+ *   peer p receives bytes_per_rank bytes from src + p * src_peer_stride_bytes
+ *     (stride 0: all-gather; stride = one block: all-to-all); with
+ *     cast_f32_to_bf16 the source is fp32 and the pushed rows are bf16.
+ *   out: [world, bytes_per_rank], slot s = the rows pushed by rank s.
+ * A peer that never arrives traps the kernel after a bounded wait (no hang).
+ * ------------------------------------------------------------------------- */
+size_t moma_peer_ctrl_bytes(void);
+int moma_peer_exchange(const void *src, int64_t src_peer_stride_bytes, int64_t bytes_per_rank,
+                       int cast_f32_to_bf16, const uint64_t *peer_bases_dev, int64_t ctrl_off,
+                       int64_t data_off, int64_t region_bytes, int rank, int world, int channel,
+                       void *out, moma_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
  * debug / test hooks (not used by the product path)
  * moma_debug_nce_tc: the tcgen05 partial kernel with an optional dump of the raw
  *   score tile S = Q . Tile^T of the first queue tile of split 0:

@@ -50,6 +50,8 @@ SIGNATURES = {
     "moma_attn_bwd_workspace_bytes": (c_size_t, [_i64, _i64, c_int]),
     "moma_attn_bwd": (c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, c_int,
                               _vp, _vp, _vp, _vp, _vp, _vp, c_size_t, _vp]),
+    "moma_peer_ctrl_bytes": (c_size_t, []),
+    "moma_peer_exchange": (c_int, [_vp, _i64, _i64, c_int, _vp, _i64, _i64, _i64, c_int, c_int, c_int, _vp, _vp]),
     "moma_linear_workspace_bytes": (c_size_t, [_i64, _i64, _i64]),
     "moma_linear_fwd": (c_int, [_vp, _vp, _vp, _i64, _i64, _i64, c_int, _vp, _vp, c_size_t, _vp]),
     "moma_linear_bwd": (c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, c_int, _vp, _vp, _vp, _vp, c_size_t, _vp]),

@@ -25,6 +25,7 @@ import torch.nn.functional as F
 
 from . import ops
 from .lazy_logits import LazyLogits
+from .peer import CH_PARTIALS, CH_QUERIES, PeerExchange
 from .mem_moco import BaseMoCo, _stale_after_enqueue
 
 
@@ -130,17 +131,28 @@ class ShardedMoCo(BaseMoCo):
         group, rank = self.group, self.rank
         memory_shard = self.memory_shard
 
+        # NVLink peer-memory exchange (one kernel per collective) where available, torch.distributed otherwise
+        peer = PeerExchange.create(group, q.device, 2 * W * bsz * (D + 4) * 4) if q.is_cuda else None
+
         def compute(q_, k_):
-            q_op, dtype, q32, k32, rnd = ops.nce_operands(q_, k_, "bf16" if use_bf16 else "fp32")
             # 1. all-gather the queries (every rank must contribute the same B_local)
-            all_q = torch.empty((W * bsz, D), dtype=q_op.dtype, device=q_.device)
-            dist.all_gather_into_tensor(all_q, q_op.contiguous(), group=group)
+            if peer is not None:
+                q32, k32 = ops._f32c(q_.detach()), ops._f32c(k_.detach())
+                dtype, rnd = (ops.BF16, True) if use_bf16 else (ops.F32, False)
+                all_q = peer.allgather(q32, CH_QUERIES, to_bf16=use_bf16)      # bf16 cast fused into the push
+            else:
+                q_op, dtype, q32, k32, rnd = ops.nce_operands(q_, k_, "bf16" if use_bf16 else "fp32")
+                all_q = torch.empty((W * bsz, D), dtype=q_op.dtype, device=q_.device)
+                dist.all_gather_into_tensor(all_q, q_op.contiguous(), group=group)
             # 2. local pass over this rank's K / W rows for all n queries, then fold the splits
             queue = shadow if use_bf16 else memory_shard
             stats, Opart = ops.nce_partial(all_q, queue, inv_T, dtype)
             packed = ops.nce_merge_packed(stats, Opart)                 # [n, D + 4] = (O | m | l | mmax | pad)
             # 3. exchange: rows are ordered by owner rank, so the records route with one all-to-all
-            recv = self._exchange(packed.view(W, bsz, D + 4))           # [W(src), bsz, D + 4]
+            if peer is not None:
+                recv = peer.alltoall(packed.view(W, bsz, D + 4), CH_PARTIALS)
+            else:
+                recv = self._exchange(packed.view(W, bsz, D + 4))       # [W(src), bsz, D + 4]
             # 4. combine with the positive column (reads the receive buffer in place)
             rows, dq, pim, mx, loss, acc = ops.nce_combine_packed(recv, q32, k32, inv_T, rnd, 1.0 / bsz)
             return loss, rows, pim, mx, acc, dq

@@ -20,10 +20,46 @@ from moma_b200 import ContrastTrainer, MoCo
 from moma_b200.sharded import ShardedMoCo
 
 
+def check_peer(rank, world):
+    """moma_peer_exchange against the NCCL collectives, bit for bit, eagerly and replayed from a CUDA graph."""
+    from moma_b200.peer import CH_KEYS, CH_PARTIALS, CH_QUERIES, PeerExchange
+    dev = torch.device("cuda", torch.cuda.current_device())
+    peer = PeerExchange.create(None, dev, 1 << 20)
+    assert peer is not None, "symmetric memory unavailable on this box"
+    torch.manual_seed(1234 + rank)
+    for it in range(6):                                  # epochs advance; both parities get reused
+        rows = 64 * (1 + it % 3)
+        x = torch.randn(rows, 128, device=dev)
+        want = torch.empty(world * rows, 128, device=dev); dist.all_gather_into_tensor(want, x)
+        assert torch.equal(peer.allgather(x, CH_KEYS), want)
+        got16 = peer.allgather(x, CH_QUERIES, to_bf16=True)
+        assert got16.dtype == torch.bfloat16 and torch.equal(got16, want.to(torch.bfloat16))
+        y = torch.randn(world, rows, 132, device=dev)
+        want2 = torch.empty_like(y); dist.all_to_all_single(want2, y)
+        assert torch.equal(peer.alltoall(y, CH_PARTIALS), want2)
+    # graph replay: the epoch lives in device memory, so one captured exchange replays correctly many times
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        x = torch.zeros(256, 128, device=dev)
+        g = torch.cuda.CUDAGraph()
+        peer.allgather(x, CH_KEYS)                        # warm-up outside the capture
+        side.synchronize()
+        with torch.cuda.graph(g, stream=side):
+            out = peer.allgather(x, CH_KEYS)
+        for it in range(5):
+            x.fill_(float(rank * 10 + it))
+            g.replay()
+            side.synchronize()
+            for r in range(world):
+                assert float(out[r * 256, 0]) == float(r * 10 + it) and float(out[r * 256 + 255, 127]) == float(r * 10 + it)
+    dist.barrier()
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    check_peer(rank, world)
     ce = torch.nn.CrossEntropyLoss()
     worst = {}
     for precision, tol in (("fp32", 1e-5), ("bf16", 1e-3)):

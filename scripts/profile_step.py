@@ -8,10 +8,17 @@ from moma_b200.graphed import GraphedStep
 
 cfg = CONFIGS[sys.argv[1] if len(sys.argv) > 1 else "C2"]
 mode = sys.argv[2] if len(sys.argv) > 2 else "seq"
-dev = torch.device("cuda", 0)
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+dev = torch.device("cuda", local)
+torch.cuda.set_device(dev)
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
+    if rank != 0:
+        sys.stdout = open(os.devnull, "w")
 torch.cuda.set_stream(torch.cuda.Stream(dev))
-cs = CriterionStep(cfg, 0, 1, dev)
-g = GraphedStep(cs.step if mode == "seq" else cs.step_overlapped, contrast=cs.contrast, rows_per_step=cfg["B"])
+cs = CriterionStep(cfg, rank, world, dev)
+g = GraphedStep(cs.step if mode == "seq" else cs.step_overlapped, contrast=cs.contrast, rows_per_step=cfg["B"] * world)
 for _ in range(5):
     g.replay()
 torch.cuda.synchronize()
