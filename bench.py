@@ -146,25 +146,38 @@ class CriterionStep:
         if self.head_ema:
             self.trainer.momentum_update(crit.embed_s, crit.embed_t, opt.alpha)
         with torch.no_grad():
-            k = crit.embed_t(feat_t)
-        all_k = self.trainer._global_gather(k) if self.world > 1 else k
+            k0 = crit.embed_t(feat_t)
         f_s = crit.embed_s(feat_s)
         f_s = crit.atts_q(f_s)
-        k = crit.atts_k(k)
+        k = crit.atts_k(k0)
         if self.world > 1:
-            # K-sharded queue: this rank only enqueues every W-th attended key -> attend those rows only
-            owned = crit.atts_queue.forward_rows(all_k, *self.contrast.owned_rows(all_k.shape[0]))
+            # K-sharded queue: this rank only enqueues every W-th attended key -> attend those rows only, and every
+            # rank projects only its own keys (the qkv projections are all-gathered instead of the raw keys)
+            owned = crit.atts_queue.forward_rows_gathered(k0, self.trainer._global_gather,
+                                                          *self.contrast.owned_rows(k0.shape[0] * self.world))
             return self._loss_and_backward(f_s, k, None, feat_s, owned_k=owned)
-        all_k = crit.atts_queue(all_k)
+        all_k = crit.atts_queue(k0)
         return self._loss_and_backward(f_s, k, all_k, feat_s)
 
-    def _loss_and_backward(self, f_s, k, all_k, feat_s, owned_k=None):
-        output = self.contrast(q=f_s, k=k, owned_k=owned_k) if owned_k is not None else \
-            self.contrast(q=f_s, k=k, all_k=all_k)
+    def _loss_and_backward(self, f_s, k, all_k, feat_s, owned_k=None, enqueue_stream=None):
+        if enqueue_stream is not None:
+            output = self.contrast(q=f_s, k=k, defer_enqueue=True)
+        else:
+            output = self.contrast(q=f_s, k=k, owned_k=owned_k) if owned_k is not None else \
+                self.contrast(q=f_s, k=k, all_k=all_k)
         losses, accs = self.trainer._compute_loss_accuracy(output[:-1], output[-1], self.ce)
         for p in self.params:
             p.grad = None
         feat_s.grad = None
+        if enqueue_stream is not None:
+            # the queue update only has to follow the InfoNCE pass that reads the old queue: it runs on the branch
+            # that produced the new keys, concurrently with the backward
+            enqueue_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(enqueue_stream), torch.no_grad():
+                if owned_k is not None:
+                    self.contrast.enqueue(owned_k=owned_k)
+                else:
+                    self.contrast.enqueue(all_k)
         losses[0].backward()
         self.loss = losses[0]
         return losses[0]
@@ -185,14 +198,14 @@ class CriterionStep:
                 self.trainer.momentum_update(crit.embed_s, crit.embed_t, opt.alpha)
             with torch.no_grad():
                 k0 = crit.embed_t(self.feat_t)
-            all_k = self.trainer._global_gather(k0) if self.world > 1 else k0
             s_u.wait_stream(s_t)
-            owned = None
+            owned = all_k = None
             with torch.cuda.stream(s_u):
                 if self.world > 1:
-                    owned = crit.atts_queue.forward_rows(all_k, *self.contrast.owned_rows(all_k.shape[0]))
+                    owned = crit.atts_queue.forward_rows_gathered(k0, self.trainer._global_gather,
+                                                                  *self.contrast.owned_rows(k0.shape[0] * self.world))
                 else:
-                    all_k = crit.atts_queue(all_k)
+                    all_k = crit.atts_queue(k0)
             k = crit.atts_k(k0)
         f_s = crit.embed_s(self.feat_s)
         # The backbone EMA (bandwidth-bound, 270 MB of traffic) is forked AFTER the projection heads: they are the only
@@ -201,8 +214,11 @@ class CriterionStep:
         with torch.cuda.stream(s_ema):
             self.trainer.momentum_update(self.student, self.teacher, opt.alpha)
         f_s = crit.atts_q(f_s)
-        main.wait_stream(s_t); main.wait_stream(s_u)
-        loss = self._loss_and_backward(f_s, k, all_k, self.feat_s, owned_k=owned)
+        # The loss of this step needs q, the local positive keys and the OLD queue -- not the keys enqueued for later
+        # steps: only the teacher branch (s_t) joins here, the queue-attention branch (s_u) joins after the backward.
+        main.wait_stream(s_t)
+        loss = self._loss_and_backward(f_s, k, all_k, self.feat_s, owned_k=owned, enqueue_stream=s_u)
+        main.wait_stream(s_u)
         main.wait_stream(s_ema)
         return loss
 

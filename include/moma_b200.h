@@ -177,7 +177,9 @@ int moma_attn_fwd(const float *x, const float *w_qkv, const float *b_qkv, const 
                   const float *b_proj, int64_t N, int64_t C, int H, float *y, float *qkv,
                   float *o, float *lse, float *attn_probs, moma_stream_t stream);
 /* Forward for the query rows q_start + i*q_stride (i < q_count) only; keys / values from all N rows.
- * y, o: [q_count, C]; lse: [H, q_count]; qkv: [N, 3C] scratch.  Forward only (no saved state). */
+ * y, o: [q_count, C]; lse: [H, q_count]; qkv: [N, 3C] scratch.  Forward only (no saved state).
+ * x == NULL (then w_qkv / b_qkv are ignored): qkv is an INPUT holding the projections of all N rows,
+ * e.g. all-gathered from the ranks that computed them (K-sharded queue: no rank projects all W*B keys). */
 int moma_attn_fwd_rows(const float *x, const float *w_qkv, const float *b_qkv, const float *w_proj,
                        const float *b_proj, int64_t N, int64_t C, int H, int64_t q_start,
                        int64_t q_stride, int64_t q_count, float *y, float *qkv, float *o, float *lse,

@@ -140,6 +140,18 @@ class Attention(nn.Module):
                                   self.num_heads, q_start, q_stride, q_count)
 
 
+    def forward_rows_gathered(self, x_local, gather, q_start, q_stride, q_count):
+        """``forward_rows`` over the concatenation of every rank's ``x_local`` without any rank projecting all of
+        it: each rank projects its own rows (qkv Linear), the projections are all-gathered (``gather``: [B, 3C] ->
+        [W * B, 3C], e.g. ContrastTrainer._global_gather) and the attention runs for the requested rows.  No autograd."""
+        with torch.no_grad():
+            if not self._fusable(x_local):
+                return self._composed(gather(x_local))[q_start::q_stride][:q_count]
+            qkv_local = ops.linear(x_local, self.qkv.weight, self.qkv.bias, key=("rows_gathered", id(self)))
+            return ops.attention_rows_from_qkv(gather(qkv_local), self.proj.weight, self.proj.bias, self.num_heads,
+                                               q_start, q_stride, q_count)
+
+
 class Attention_viz(Attention):
     """reference :171-197: also returns the attention map [1, H, N, N]."""
 

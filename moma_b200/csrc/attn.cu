@@ -664,14 +664,15 @@ extern "C" __attribute__((visibility("default"))) int moma_attn_fwd_rows(
     float* lse, moma_stream_t stream) {
     int rc = check_attn("attn_fwd_rows", N, C, H);
     if (rc != MOMA_OK) return rc;
-    MOMA_REQUIRE(x && w_qkv && w_proj && b_proj && y && qkv && o && lse, MOMA_ERR_INVALID, "attn_fwd_rows: null pointer");
+    MOMA_REQUIRE((x == nullptr || w_qkv) && w_proj && b_proj && y && qkv && o && lse, MOMA_ERR_INVALID, "attn_fwd_rows: null pointer");
     MOMA_REQUIRE(q_count > 0 && q_stride > 0 && q_start >= 0 && q_start + (q_count - 1) * q_stride < N, MOMA_ERR_INVALID,
                  "attn_fwd_rows: row subset out of range");
     MOMA_REQUIRE(aligned16(qkv) && aligned16(o), MOMA_ERR_ALIGN, "attn_fwd_rows: qkv/o must be 16-byte aligned");
     cudaStream_t st = as_stream(stream);
     const int n = (int)N, c = (int)C, hd = c / H, nq = (int)q_count;
     const float scale = 1.0f / sqrtf((float)hd);
-    sgemm(x, C, 1, w_qkv, C, 1, b_qkv, qkv, 3 * C, n, 3 * c, c, st);
+    // x == NULL: qkv already holds the projections of all N tokens (e.g. all-gathered from the ranks that own them)
+    if (x != nullptr) sgemm(x, C, 1, w_qkv, C, 1, b_qkv, qkv, 3 * C, n, 3 * c, c, st);
     switch (hd) {
         case 8: launch_fwd<8>(qkv, n, c, H, scale, o, lse, st, (int)q_start, (int)q_stride, nq); break;
         case 16: launch_fwd<16>(qkv, n, c, H, scale, o, lse, st, (int)q_start, (int)q_stride, nq); break;
@@ -681,7 +682,7 @@ extern "C" __attribute__((visibility("default"))) int moma_attn_fwd_rows(
     }
     sgemm(o, C, 1, w_proj, C, 1, b_proj, y, C, nq, c, c, st);
     MOMA_CUDA_LAUNCH_CHECK("attn_fwd_rows");
-    note_launches(3);
+    note_launches(x != nullptr ? 3 : 2);
     return MOMA_OK;
 }
 

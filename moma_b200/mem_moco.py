@@ -155,26 +155,37 @@ class MoCo(BaseMoCo):
         self.memory = F.normalize(self.memory)
         self.track_overwritten = False      # set True to allow materialising logits after the enqueue
 
-    def forward(self, q, k, all_k=None):
+    def forward(self, q, k, all_k=None, defer_enqueue=False):
         """
         Args:
           q: query on current node
           k: key on current node
           all_k: gather of feats across nodes; otherwise use k
+          defer_enqueue: (extension) skip the queue update here; the caller runs ``enqueue(all_k)`` later in the
+            step.  The loss of a step does not depend on the keys it enqueues, so a scheduler can take the branch
+            that produces ``all_k`` (the queue attention) off the critical path.
         Returns (logits, labels) as mem_moco.py:77-100.
         """
         bsz = q.size(0)
         k = k.detach()
         labels = self._labels(bsz, q.device)
         logits = self._fused_logits(q, k, self.memory, labels)
+        if defer_enqueue:
+            if isinstance(logits, LazyLogits) and not self.track_overwritten:
+                logits._materialize = _stale_after_enqueue
+            return logits, labels
         all_k = all_k if all_k is not None else k
         if self.track_overwritten:
             self._remember_overwritten([logits], self.memory, all_k.size(0))
         elif isinstance(logits, LazyLogits):
             logits._materialize = _stale_after_enqueue
+        self.enqueue(all_k)
+        return logits, labels
+
+    def enqueue(self, all_k):
+        """The queue update of forward (reference mem_moco.py:14-27, :97-99) on its own."""
         self._update_memory(all_k, self.memory)
         self._update_pointer(all_k.size(0))
-        return logits, labels
 
 
 def _stale_after_enqueue():

@@ -443,6 +443,21 @@ def attention_rows(x, w_qkv, b_qkv, w_proj, b_proj, num_heads: int, q_start: int
     return y
 
 
+def attention_rows_from_qkv(qkv, w_proj, b_proj, num_heads: int, q_start: int, q_stride: int, q_count: int):
+    """As attention_rows, from precomputed projections qkv [N, 3C] of all N tokens (forward only)."""
+    _need_cuda(qkv, w_proj)
+    with torch.no_grad():
+        qc, wp, bp = _f32c(qkv), _f32c(w_proj), _f32c(b_proj)
+        N, C = qc.shape[0], qc.shape[1] // 3
+        dev = qc.device
+        y = torch.empty((q_count, C), dtype=torch.float32, device=dev)
+        o = torch.empty((q_count, C), dtype=torch.float32, device=dev)
+        lse = torch.empty((num_heads, q_count), dtype=torch.float32, device=dev)
+        check(_lib.load().moma_attn_fwd_rows(None, None, None, _p(wp), _p(bp), N, C, int(num_heads), int(q_start),
+                                             int(q_stride), int(q_count), _p(y), _p(qc), _p(o), _p(lse), _stream()))
+    return y
+
+
 def attention_supported(C: int, H: int) -> bool:
     return C % H == 0 and (C // H) in (8, 16, 32, 64, 128)
 

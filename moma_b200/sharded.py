@@ -116,9 +116,10 @@ class ShardedMoCo(BaseMoCo):
             raise ValueError("owned_rows needs n % world == 0")
         return (self.rank - self.index) % W, W, n // W
 
-    def forward(self, q, k, all_k=None, owned_k=None):
+    def forward(self, q, k, all_k=None, owned_k=None, defer_enqueue=False):
         """As MoCo.forward.  ``owned_k`` (optional, instead of ``all_k``): only the rows
-        ``owned_rows(n)`` of the step's keys, e.g. from ``Attention.forward_rows``."""
+        ``owned_rows(n)`` of the step's keys, e.g. from ``Attention.forward_rows``.  ``defer_enqueue``: skip the
+        queue update; the caller runs ``enqueue(all_k=... | owned_k=...)`` later in the step."""
         bsz, D = q.shape
         W = self.world
         k = k.detach()
@@ -160,8 +161,16 @@ class ShardedMoCo(BaseMoCo):
         nce = ops.nce_fused(q, k, compute)
         shape = (bsz, self.K + 1) if bsz != 1 else (self.K + 1,)
         logits = LazyLogits(shape, q.device, nce, labels, _stale_after_enqueue)
-        # 5. enqueue the rows this rank owns
+        if not defer_enqueue:
+            self.enqueue(all_k=all_k if all_k is not None else k, owned_k=owned_k)
+        return logits, labels
+
+    def enqueue(self, all_k=None, owned_k=None):
+        """5. enqueue the rows this rank owns (from the full key list or from the owned rows only)."""
+        W = self.world
+        use_bf16 = ops.get_precision() == "bf16" and ops.bf16_supported(self.n_dim)
         with torch.no_grad():
+            shadow = self._shadow_of(self.memory_shard) if use_bf16 else None
             sh = shadow if use_bf16 else self._shadow_of(self.memory_shard, create=False)
             if owned_k is not None:
                 n = owned_k.shape[0] * W
@@ -169,11 +178,9 @@ class ShardedMoCo(BaseMoCo):
                 ops.enqueue(owned_k, self.memory_shard, sh, self.K, self.index, rank=self.rank, world=W,
                             index_dev=self._index_dev, key_start=start, key_stride=stride)
             else:
-                all_k = all_k if all_k is not None else k
                 n = all_k.shape[0]
                 if n > self.K:
                     raise RuntimeError("enqueue of more rows than K (duplicate ids)")
                 ops.enqueue(all_k, self.memory_shard, sh, self.K, self.index, rank=self.rank, world=W,
                             index_dev=self._index_dev)
         self._update_pointer(n)
-        return logits, labels

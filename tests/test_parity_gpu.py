@@ -540,6 +540,14 @@ def test_attention_row_subset_and_strided_enqueue(ops):
         count = (200 - start + stride - 1) // stride
         sub = att.forward_rows(x, start, stride, count)
         assert torch.allclose(sub, full[start::stride], rtol=1e-5, atol=1e-6), (start, stride)
+        # the K-sharded variant: per-rank projections, gathered (here: two "ranks" holding x[:100] / x[100:])
+        parts = {}
+
+        def fake_gather(qkv_local, parts=parts):
+            parts.setdefault("other", att.qkv(x[100:]).detach())
+            return torch.cat([qkv_local, parts["other"]], dim=0)
+        sub2 = att.forward_rows_gathered(x[:100].contiguous(), fake_gather, start, stride, count)
+        assert torch.allclose(sub2, full[start::stride], rtol=1e-5, atol=1e-6), (start, stride)
     rng = np.random.default_rng(5)
     K, D, n, W = 64, 32, 16, 4
     full_q = rng.standard_normal((K, D)).astype(np.float32)
@@ -614,3 +622,28 @@ def test_linear_is_deterministic_and_head_uses_it():
     ref = torch.nn.Sequential(*list(crit.embed_s))        # plain torch modules over the same parameters
     yr = ref(x.detach())
     assert float((y1 - yr).norm() / yr.norm()) < 2e-6
+
+
+@pytest.mark.gpu
+def test_deferred_enqueue_equals_inline():
+    """forward(..., defer_enqueue=True) + enqueue(all_k) leaves the same loss, gradient, queue and pointer as the
+    reference-ordered forward (mem_moco.py:77-100): the step's loss never reads the keys it enqueues."""
+    import torch
+    from moma_b200 import MoCo
+    torch.manual_seed(3)
+    a = MoCo(128, 1024, 0.15).cuda()
+    torch.manual_seed(3)
+    b = MoCo(128, 1024, 0.15).cuda()
+    a.index = b.index = 1000                      # wraps
+    ce = torch.nn.CrossEntropyLoss()
+    for _ in range(2):
+        q1 = torch.randn(48, 128, device="cuda", requires_grad=True)
+        q2 = q1.detach().clone().requires_grad_()
+        k = torch.randn(48, 128, device="cuda")
+        all_k = torch.randn(96, 128, device="cuda")
+        la, lab = a(q1, k, all_k)
+        lb, lbb = b(q2, k, defer_enqueue=True)
+        ce(la, lab).backward()
+        ce(lb, lbb).backward()
+        b.enqueue(all_k)
+        assert torch.equal(q1.grad, q2.grad) and torch.equal(a.memory, b.memory) and a.index == b.index
