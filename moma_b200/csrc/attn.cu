@@ -122,26 +122,6 @@ static void sgemm(const float* A, int64_t a_rs, int64_t a_cs, const float* Bm, i
     else sgemm_tm<16>(A, a_rs, a_cs, Bm, b_rs, b_cs, bias, Cm, ldc, M, N, K, st);
 }
 
-// column sums: out[c] = sum_r X[r, c]   (bias gradients)
-__global__ void __launch_bounds__(256)
-colsum_kernel(const float* __restrict__ X, int rows, int cols, float* __restrict__ out) {
-    pdl_wait();
-    pdl_launch_dependents();
-    __shared__ float red[8][32 + 1];
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int ry = threadIdx.x >> 5;
-    float s = 0.f;
-    if (c < cols)
-        for (int r = ry; r < rows; r += 8) s += X[(int64_t)r * cols + c];
-    red[ry][threadIdx.x & 31] = s;
-    __syncthreads();
-    if (ry == 0 && c < cols) {
-        float t = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-        out[c] = t;
-    }
-}
 
 // ------------------------------------------------------------------ fused attention core
 // Tiles: 4*RW "row" tokens per CTA (RW per warp, 4 warps) against KT "column" tokens per step.  KT is
@@ -718,7 +698,7 @@ extern "C" __attribute__((visibility("default"))) int moma_attn_bwd(const float*
     cudaStream_t s1 = bs.ok ? bs.s1 : st, s2 = bs.ok ? bs.s2 : st;
     if (bs.ok) { cudaEventRecord(bs.fork, st); cudaStreamWaitEvent(s1, bs.fork, 0); }
     // proj backward: dW_proj[co, ci] = sum_n dy[n, co] o[n, ci];  db = colsum(dy);  dO = dy W_proj
-    if (grad_b_proj) launch_pdl(colsum_kernel, dim3((c + 31) / 32), dim3(256), 0, s1, grad_y, n, c, grad_b_proj);
+    if (grad_b_proj) colsum_masked(grad_y, nullptr, n, c, grad_b_proj, s1);
     if (grad_w_proj) sgemm(grad_y, 1, C, o, 1, C, nullptr, grad_w_proj, C, c, c, n, s1);
     sgemm(grad_y, C, 1, w_proj, 1, C, nullptr, dO, C, n, c, c, st);
     launch_pdl(attn_delta_kernel, dim3((n * H + 3) / 4), dim3(128), 0, st, dO, o, n, c, H, delta);
@@ -735,7 +715,7 @@ extern "C" __attribute__((visibility("default"))) int moma_attn_bwd(const float*
         cudaEventRecord(bs.dkv, s2); cudaStreamWaitEvent(st, bs.dkv, 0);    // st too
     }
     // qkv backward: dW_qkv[j, ci] = sum_n dqkv[n, j] x[n, ci]; db = colsum(dqkv); dx = dqkv W_qkv
-    if (grad_b_qkv) launch_pdl(colsum_kernel, dim3((3 * c + 31) / 32), dim3(256), 0, s2, dqkv, n, 3 * c, grad_b_qkv);
+    if (grad_b_qkv) colsum_masked(dqkv, nullptr, n, 3 * c, grad_b_qkv, s2);
     if (grad_w_qkv) sgemm(dqkv, 1, 3 * C, x, 1, C, nullptr, grad_w_qkv, C, 3 * c, c, n, s2);
     if (grad_x) sgemm(dqkv, 3 * C, 1, w_qkv, 1, C, nullptr, grad_x, C, n, c, 3 * c, st);
     if (bs.ok) {                                                             // join

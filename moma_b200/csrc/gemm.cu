@@ -225,26 +225,44 @@ gemm3xtf32_kernel(const GemmParams p) {
     if (tid == 0) p.tickets[tile] = 0u;
 }
 
-// column sums of a (masked) [rows, cols] matrix: bias gradients
+// column sums of a (masked) [rows, cols] matrix: bias gradients.  8 columns per CTA (cols / 8 CTAs), 32 row phases:
+// a thread sums every 32nd row of one column with its loads unrolled (one memory round trip for the usual 256-row batch),
+// then the 32 phases are added in a fixed order (deterministic).
+constexpr int kCsCols = 8, kCsPhases = 32;
 __global__ void __launch_bounds__(256)
 colsum_masked_kernel(const float* __restrict__ X, const float* __restrict__ mask, int rows, int cols, float* __restrict__ out) {
     pdl_wait();
     pdl_launch_dependents();
-    __shared__ float red[8][32 + 1];
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int ry = threadIdx.x >> 5;
+    __shared__ float red[kCsPhases][kCsCols + 1];
+    const int cl = threadIdx.x & (kCsCols - 1), ph = threadIdx.x >> 3;
+    const int c = blockIdx.x * kCsCols + cl;
     float s = 0.f;
-    if (c < cols)
-        for (int r = ry; r < rows; r += 8) {
+    if (c < cols) {
+        int r = ph;
+        for (; r + 7 * kCsPhases < rows; r += 8 * kCsPhases) {
+            float v[8], m[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = X[(int64_t)(r + u * kCsPhases) * cols + c];
+            if (mask) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) m[u] = mask[(int64_t)(r + u * kCsPhases) * cols + c];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = m[u] > 0.f ? v[u] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+        }
+        for (; r < rows; r += kCsPhases) {
             const float v = X[(int64_t)r * cols + c];
             s += (mask == nullptr || mask[(int64_t)r * cols + c] > 0.f) ? v : 0.f;
         }
-    red[ry][threadIdx.x & 31] = s;
+    }
+    red[ph][cl] = s;
     __syncthreads();
-    if (ry == 0 && c < cols) {
+    if (threadIdx.x < kCsCols && c < cols) {
         float tot = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) tot += red[i][threadIdx.x];
+        for (int i = 0; i < kCsPhases; ++i) tot += red[i][threadIdx.x];
         out[c] = tot;
     }
 }
@@ -304,7 +322,7 @@ int gemm_nt(const float* A, const float* a_mask, int64_t a_rs, int64_t a_cs, con
 }
 
 void colsum_masked(const float* X, const float* mask, int rows, int cols, float* out, cudaStream_t st) {
-    launch_pdl(colsum_masked_kernel, dim3((cols + 31) / 32), dim3(256), 0, st, X, mask, rows, cols, out);
+    launch_pdl(colsum_masked_kernel, dim3((cols + kCsCols - 1) / kCsCols), dim3(256), 0, st, X, mask, rows, cols, out);
 }
 
 }  // namespace moma
