@@ -2,9 +2,9 @@
 MoMA/criterion_moco_att.py (same class names, constructor arguments, sub-module
 and parameter names, construction order -> identical RNG draws and state_dict).
 
-``Normalize`` and the ``Attention`` family run on the sm_100a kernels behind
-include/moma_b200.h; the projection-head Linears stay ``nn.Linear`` (library
-GEMMs, outside the rewritten path -- SURVEY 8a a11).
+``Normalize``, the ``Attention`` family and the projection heads' Linear(+ReLU) layers
+run on the sm_100a kernels behind include/moma_b200.h; the modules keep their ``nn.Linear``
+parameters (same state_dict), only the computation is routed.
 """
 from __future__ import annotations
 
