@@ -208,10 +208,15 @@ class _Head(nn.Sequential):
             m = mods[i]
             if isinstance(m, nn.Linear) and x.dim() == 2:
                 if self._tf32_library(m):
+                    relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU) and m.bias is not None
                     prev = torch.backends.cuda.matmul.allow_tf32
                     torch.backends.cuda.matmul.allow_tf32 = True
                     try:
-                        x = m(x)
+                        if relu:        # bias + ReLU in the GEMM epilogue (one launch instead of two)
+                            x = torch._addmm_activation(m.bias, x, m.weight.t(), use_gelu=False)
+                            i += 1
+                        else:
+                            x = m(x)
                     finally:
                         torch.backends.cuda.matmul.allow_tf32 = prev
                 else:

@@ -453,13 +453,18 @@ attn_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
     };
     load_rows_async<HD>(k_s, qkv + C + h * HD, ldg, j0, kAR, N);
     load_rows_async<HD>(v_s, qkv + 2 * C + h * HD, ldg, j0, kAR, N);
-    issue_qd(0, 0);
+    issue_qd(0, (int)((long long)((N + KT - 1) / KT) * blockIdx.z / gridDim.z) * KT);
     float acc_k[Cfg::RPL][Cfg::CPL] = {};
     float acc_v[Cfg::RPL][Cfg::CPL] = {};
-    for (int i0 = 0, it = 0; i0 < N; i0 += KT, ++it) {
+    // gridDim.z == 2: the query tiles are split between two CTAs whose results are added into a zeroed dK/dV
+    // (exactly two addends per element: the sum does not depend on their order -> still deterministic)
+    const int n_tiles = (N + KT - 1) / KT;
+    const int t_begin = (int)((long long)n_tiles * blockIdx.z / gridDim.z), t_end = (int)((long long)n_tiles * (blockIdx.z + 1) / gridDim.z);
+    const int i_end = min(N, t_end * KT);
+    for (int i0 = t_begin * KT, it = 0; i0 < i_end; i0 += KT, ++it) {
         cp_async_wait<0>();
         __syncthreads();
-        if (i0 + KT < N) issue_qd((it + 1) & 1, i0 + KT);
+        if (i0 + KT < i_end) issue_qd((it + 1) & 1, i0 + KT);
         const float* q_s = qd_s + (2 * (it & 1)) * KT * Cfg::LD;
         const float* do_s = q_s + KT * Cfg::LD;
         float lse_c[CC], del_c[CC];                          // issued before the dot products: their latency hides there
@@ -495,8 +500,10 @@ attn_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
         if (row < N)
 #pragma unroll
             for (int c = 0; c < Cfg::CPL; ++c) {
-                dqkv[(int64_t)row * ldg + C + h * HD + cbase + 32 * c] = acc_k[r][c] * scale;
-                dqkv[(int64_t)row * ldg + 2 * C + h * HD + cbase + 32 * c] = acc_v[r][c];
+                float* pk = dqkv + (int64_t)row * ldg + C + h * HD + cbase + 32 * c;
+                float* pv = dqkv + (int64_t)row * ldg + 2 * C + h * HD + cbase + 32 * c;
+                if (gridDim.z == 1) { *pk = acc_k[r][c] * scale; *pv = acc_v[r][c]; }
+                else { atomicAdd(pk, acc_k[r][c] * scale); atomicAdd(pv, acc_v[r][c]); }
             }
     }
 }
@@ -525,7 +532,7 @@ static void launch_fwd_rw(const float* qkv, int N, int C, int H, float scale, fl
 }
 template <int HD, int RW>
 static void launch_bwd_rw(const float* qkv, const float* dO, const float* lse, const float* delta, int N, int C, int H,
-                          float scale, float* dqkv, cudaStream_t st, cudaStream_t st2) {
+                          float scale, float* dqkv, cudaStream_t st, cudaStream_t st2, bool dkv_split) {
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(attn_bwd_dq_kernel<HD, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dq_smem<HD, RW>());
@@ -536,8 +543,10 @@ static void launch_bwd_rw(const float* qkv, const float* dO, const float* lse, c
     const dim3 grid((N + AR - 1) / AR, H);
     // dQ and dK/dV are independent: two streams (st2 was forked from st by the caller)
     launch_pdl(attn_bwd_dq_kernel<HD, RW>, grid, dim3(kAThreads), dq_smem<HD, RW>(), st, qkv, dO, lse, delta, N, C, scale, dqkv);
-    launch_pdl(attn_bwd_dkv_kernel<HD, RW>, grid, dim3(kAThreads), dkv_smem<HD, RW>(), st2, qkv, dO, lse, delta, N, C, scale, dqkv);
+    launch_pdl(attn_bwd_dkv_kernel<HD, RW>, dim3(grid.x, grid.y, dkv_split ? 2 : 1), dim3(kAThreads), dkv_smem<HD, RW>(), st2,
+               qkv, dO, lse, delta, N, C, scale, dqkv);
 }
+
 
 // rows per warp: the largest of {8, 4, 2} (but RW * HD >= 32) that still gives about one CTA per SM.  (One row per
 // warp -- two CTAs per SM -- was measured: each warp still reads the whole key tile from shared memory, so the
@@ -560,14 +569,22 @@ static void launch_fwd(const float* qkv, int N, int C, int H, float scale, float
                  else launch_fwd_rw<HD, 4>(qkv, N, C, H, scale, o, lse, st, q_start, q_stride, NQ);
     }
 }
+// dK/dV is the longest kernel of the backward (twice the work of dQ): split its query loop over two CTAs when
+// there are at least two query tiles and the grid is at most one wave (the caller then zeroes dK/dV first)
+template <int HD>
+static bool dkv_wants_split(int N, int H) {
+    const int rw = pick_rw<HD>(N, H);
+    constexpr int KT = HD <= 32 ? 128 : 64;                 // AttnCfg::KT_BWD
+    return (N + KT - 1) / KT >= 2 && ((N + 4 * rw - 1) / (4 * rw)) * H <= sm_count();
+}
 template <int HD>
 static void launch_bwd(const float* qkv, const float* dO, const float* lse, const float* delta, int N, int C, int H,
-                       float scale, float* dqkv, cudaStream_t st, cudaStream_t st2) {
+                       float scale, float* dqkv, cudaStream_t st, cudaStream_t st2, bool dkv_split) {
     switch (pick_rw<HD>(N, H)) {
-        case 8: launch_bwd_rw<HD, 8>(qkv, dO, lse, delta, N, C, H, scale, dqkv, st, st2); break;
-        case 4: launch_bwd_rw<HD, 4>(qkv, dO, lse, delta, N, C, H, scale, dqkv, st, st2); break;
-        default: if constexpr (HD >= 16) launch_bwd_rw<HD, 2>(qkv, dO, lse, delta, N, C, H, scale, dqkv, st, st2);
-                 else launch_bwd_rw<HD, 4>(qkv, dO, lse, delta, N, C, H, scale, dqkv, st, st2);
+        case 8: launch_bwd_rw<HD, 8>(qkv, dO, lse, delta, N, C, H, scale, dqkv, st, st2, dkv_split); break;
+        case 4: launch_bwd_rw<HD, 4>(qkv, dO, lse, delta, N, C, H, scale, dqkv, st, st2, dkv_split); break;
+        default: if constexpr (HD >= 16) launch_bwd_rw<HD, 2>(qkv, dO, lse, delta, N, C, H, scale, dqkv, st, st2, dkv_split);
+                 else launch_bwd_rw<HD, 4>(qkv, dO, lse, delta, N, C, H, scale, dqkv, st, st2, dkv_split);
     }
 }
 
@@ -697,6 +714,18 @@ extern "C" __attribute__((visibility("default"))) int moma_attn_bwd(const float*
     BwdStreams& bs = bwd_streams();
     cudaStream_t s1 = bs.ok ? bs.s1 : st, s2 = bs.ok ? bs.s2 : st;
     if (bs.ok) { cudaEventRecord(bs.fork, st); cudaStreamWaitEvent(s1, bs.fork, 0); }
+    bool split = false;
+    switch (hd) {
+        case 8: split = dkv_wants_split<8>(n, H); break;
+        case 16: split = dkv_wants_split<16>(n, H); break;
+        case 32: split = dkv_wants_split<32>(n, H); break;
+        case 64: split = dkv_wants_split<64>(n, H); break;
+        default: split = dkv_wants_split<128>(n, H); break;
+    }
+    if (split) {          // dK/dV are accumulated by two CTAs each: zero them early, off the critical path
+        if (bs.ok) cudaStreamWaitEvent(s2, bs.fork, 0);
+        cudaMemset2DAsync(dqkv + C, (size_t)3 * C * sizeof(float), 0, (size_t)2 * C * sizeof(float), (size_t)N, s2);
+    }
     // proj backward: dW_proj[co, ci] = sum_n dy[n, co] o[n, ci];  db = colsum(dy);  dO = dy W_proj
     if (grad_b_proj) colsum_masked(grad_y, nullptr, n, c, grad_b_proj, s1);
     if (grad_w_proj) sgemm(grad_y, 1, C, o, 1, C, nullptr, grad_w_proj, C, c, c, n, s1);
@@ -704,11 +733,11 @@ extern "C" __attribute__((visibility("default"))) int moma_attn_bwd(const float*
     launch_pdl(attn_delta_kernel, dim3((n * H + 3) / 4), dim3(128), 0, st, dO, o, n, c, H, delta);
     if (bs.ok) { cudaEventRecord(bs.d_o, st); cudaStreamWaitEvent(s2, bs.d_o, 0); }
     switch (hd) {
-        case 8: launch_bwd<8>(qkv, dO, lse, delta, n, c, H, scale, dqkv, st, s2); break;
-        case 16: launch_bwd<16>(qkv, dO, lse, delta, n, c, H, scale, dqkv, st, s2); break;
-        case 32: launch_bwd<32>(qkv, dO, lse, delta, n, c, H, scale, dqkv, st, s2); break;
-        case 64: launch_bwd<64>(qkv, dO, lse, delta, n, c, H, scale, dqkv, st, s2); break;
-        default: launch_bwd<128>(qkv, dO, lse, delta, n, c, H, scale, dqkv, st, s2); break;
+        case 8: launch_bwd<8>(qkv, dO, lse, delta, n, c, H, scale, dqkv, st, s2, split); break;
+        case 16: launch_bwd<16>(qkv, dO, lse, delta, n, c, H, scale, dqkv, st, s2, split); break;
+        case 32: launch_bwd<32>(qkv, dO, lse, delta, n, c, H, scale, dqkv, st, s2, split); break;
+        case 64: launch_bwd<64>(qkv, dO, lse, delta, n, c, H, scale, dqkv, st, s2, split); break;
+        default: launch_bwd<128>(qkv, dO, lse, delta, n, c, H, scale, dqkv, st, s2, split); break;
     }
     if (bs.ok) {
         cudaEventRecord(bs.dq, st);  cudaStreamWaitEvent(s2, bs.dq, 0);     // s2 now has dQ and dK/dV

@@ -973,7 +973,10 @@ int nce_tc_num_splits(int64_t B, int64_t D, int64_t K_local) {
     const int64_t mgroups = (B + nq * tc::kBM - 1) / (nq * tc::kBM);
     const int64_t tiles = (K_local + bn - 1) / bn;
     int64_t s = sm_count() / mgroups;
-    if (s > tiles) s = tiles;
+    // at least two queue tiles per CTA: below that a CTA is all fixed cost and the combine kernel reads twice the partials
+    // (C2 step: 166.3 us with 1, 162.8 us with 2, 162.7 us with 4); MOMA_B200_NCE_MIN_TILES overrides
+    static const int min_tiles = [] { const char* e = getenv("MOMA_B200_NCE_MIN_TILES"); int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
+    if (s > tiles / min_tiles) s = tiles / min_tiles;
     if (s < 1) s = 1;
     return (int)s;
 }
