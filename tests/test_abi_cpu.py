@@ -91,6 +91,37 @@ def test_splits_heuristic_is_host_side(lib):
     assert lib.moma_attn_bwd_workspace_bytes(512, 128, 4) >= (512 * 128 * 4 + 4 * 512) * 4
 
 
+def test_linear_and_peer_validation_is_host_side(lib):
+    """Argument checks of the newer entry points return before any CUDA call (no GPU here)."""
+    assert lib.moma_linear_fwd(None, None, None, 4, 4, 4, 0, None, None, 0, None) == -1
+    assert b"null pointer" in lib.moma_last_error()
+    assert lib.moma_linear_fwd(16, 16, None, 0, 4, 4, 0, 16, None, 0, None) == -1 and b"bad shape" in lib.moma_last_error()
+    assert lib.moma_linear_bwd(16, 16, None, 16, 4, 4, 4, 1, None, None, None, None, 0, None) == -1   # relu without y
+    # split-K workspace: a 256 x 128 output over K = 512 is split (32 tiles on 148 SMs): room for >= 2 partial tiles
+    assert lib.moma_linear_workspace_bytes(256, 128, 512) > 2 * 256 * 128 * 4
+    assert lib.moma_linear_workspace_bytes(0, 1, 1) == 0
+    ctrl = lib.moma_peer_ctrl_bytes()
+    assert ctrl >= 48 and ctrl % 256 == 0
+    args = dict(src=16, stride=0, nbytes=256, cast=0, bases=16, ctrl_off=0, data_off=256, region=1 << 20, rank=0, world=2, ch=0, out=16)
+
+    def call(**kw):
+        a = dict(args, **kw)
+        return lib.moma_peer_exchange(a["src"], a["stride"], a["nbytes"], a["cast"], a["bases"], a["ctrl_off"], a["data_off"],
+                                      a["region"], a["rank"], a["world"], a["ch"], a["out"], None)
+    assert call(world=17) == -1 and b"max world" in lib.moma_last_error()
+    assert call(rank=2) == -1
+    assert call(ch=4) == -1 and b"channel" in lib.moma_last_error()
+    assert call(nbytes=100) == -2 and b"multiples of 16" in lib.moma_last_error()
+    assert call(region=512) == -5 and b"region too small" in lib.moma_last_error()       # needs 2 x world x bytes
+    assert call(src=None) == -1
+
+
+def test_peer_exchange_unavailable_without_cuda():
+    import torch
+    from moma_b200.peer import PeerExchange
+    assert PeerExchange.create(None, torch.device("cpu"), 1 << 20) is None
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "_lib", None)
     monkeypatch.setattr(_build, "LIB_PATH", str(tmp_path / "nope.so"))

@@ -82,9 +82,10 @@ def _worker(rank, world, port, ret):
     q = torch.randn(4, 16, requires_grad=True); k = torch.randn(4, 16)
     all_k = ContrastTrainer._global_gather(k)
     m.index = 28
-    logits, labels = m(q, k, all_k)
+    logits, labels = m(q, k, defer_enqueue=True)              # the queue update is scheduled after the backward
     losses, accs = ContrastTrainer._compute_loss_accuracy([logits], labels, torch.nn.CrossEntropyLoss())
     losses[0].backward()
+    m.enqueue(all_k=all_k)
     sd = m.state_dict()                                       # collective: gathers the full queue
     ret[rank] = dict(mem0=mem0.numpy(), mem1=sd["memory"].numpy(), index=m.index, loss=losses[0].item(),
                      acc=accs[0].item(), dq=q.grad.numpy(), all_k=all_k.numpy(), shape=tuple(logits.shape),
