@@ -16,7 +16,7 @@ if world > 1:
     dist.init_process_group("nccl", device_id=dev)
     if rank != 0:
         sys.stdout = open(os.devnull, "w")
-torch.cuda.set_stream(torch.cuda.Stream(dev))
+torch.cuda.set_stream(torch.cuda.Stream(dev, priority=-1))
 cs = CriterionStep(cfg, rank, world, dev)
 g = GraphedStep(cs.step if mode == "seq" else cs.step_overlapped, contrast=cs.contrast, rows_per_step=cfg["B"] * world)
 for _ in range(5):
