@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MOMA_ABI_VERSION 1
+#define MOMA_ABI_VERSION 2
 
 typedef void *moma_stream_t; /* cudaStream_t / CUstream */
 
@@ -171,11 +171,13 @@ int moma_nce_logits_qk(const float *q, const float *kpos, int64_t B, int64_t D, 
  * x [N, C]; w_qkv [3C, C]; b_qkv [3C] or NULL; w_proj [C, C]; b_proj [C].
  * Saved for backward (caller-owned): qkv [N, 3C], o [N, C] (merged heads),
  * lse [H, N].  attn_probs (nullable, [H, N, N]) is only for Attention_viz.
+ * y_bf16 (nullable, [N, C] bf16): y rounded to bf16, written by the projection's
+ * epilogue -- the operand the tcgen05 InfoNCE kernel reads (no separate cast launch).
  * head_dim = C / H must be one of 8, 16, 32, 64, 128.
  * ------------------------------------------------------------------------- */
 int moma_attn_fwd(const float *x, const float *w_qkv, const float *b_qkv, const float *w_proj,
                   const float *b_proj, int64_t N, int64_t C, int H, float *y, float *qkv,
-                  float *o, float *lse, float *attn_probs, moma_stream_t stream);
+                  float *o, float *lse, float *attn_probs, void *y_bf16, moma_stream_t stream);
 /* Forward for the query rows q_start + i*q_stride (i < q_count) only; keys / values from all N rows.
  * y, o: [q_count, C]; lse: [H, q_count]; qkv: [N, 3C] scratch.  Forward only (no saved state).
  * x == NULL (then w_qkv / b_qkv are ignored): qkv is an INPUT holding the projections of all N rows,

@@ -12,7 +12,7 @@ from ctypes import (POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_
 from . import _build
 
 F32, BF16 = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _vp = c_void_p
 _i64 = c_int64
@@ -42,7 +42,7 @@ SIGNATURES = {
                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "moma_nce_logits": (c_int, [_vp, _vp, _vp, _i64, _i64, _i64, c_float, c_int, _vp, _vp]),
     "moma_nce_logits_qk": (c_int, [_vp, _vp, _i64, _i64, c_float, _vp, _vp]),
-    "moma_attn_fwd": (c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "moma_attn_fwd": (c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "moma_debug_nce_tc": (c_int, [_vp, _vp, _i64, _i64, _i64, c_float, c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "moma_debug_tc_error": (c_int, []),
     "moma_debug_launch_count": (ctypes.c_longlong, [c_int]),

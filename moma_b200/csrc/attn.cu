@@ -112,9 +112,9 @@ static void sgemm_tm(const float* A, int64_t a_rs, int64_t a_cs, const float* Bm
 
 static void sgemm(const float* A, int64_t a_rs, int64_t a_cs, const float* Bm, int64_t b_rs,
                   int64_t b_cs, const float* bias, float* Cm, int64_t ldc, int M, int N, int K,
-                  cudaStream_t st) {
+                  cudaStream_t st, void* c_bf16 = nullptr) {
     if (!use_simt_gemm()) {      // tensor-core path (3xTF32, gemm.cu); single split: no workspace here
-        gemm_nt(A, nullptr, a_rs, a_cs, Bm, b_rs, b_cs, bias, Cm, ldc, M, N, K, 0, nullptr, 0, st);
+        gemm_nt(A, nullptr, a_rs, a_cs, Bm, b_rs, b_cs, bias, Cm, ldc, M, N, K, 0, nullptr, 0, st, c_bf16);
         return;
     }
     const int ctas32 = ((N + kGN - 1) / kGN) * ((M + 31) / 32);
@@ -623,9 +623,11 @@ static int check_attn(const char* who, int64_t N, int64_t C, int H) {
 
 using namespace moma;
 
+static inline bool ldc_is_dense(int64_t ldc, int n) { return ldc == n; }
+
 extern "C" __attribute__((visibility("default"))) int moma_attn_fwd(const float* x, const float* w_qkv, const float* b_qkv,
                              const float* w_proj, const float* b_proj, int64_t N, int64_t C, int H,
-                             float* y, float* qkv, float* o, float* lse, float* attn_probs,
+                             float* y, float* qkv, float* o, float* lse, float* attn_probs, void* y_bf16,
                              moma_stream_t stream) {
     int rc = check_attn("attn_fwd", N, C, H);
     if (rc != MOMA_OK) return rc;
@@ -646,7 +648,12 @@ extern "C" __attribute__((visibility("default"))) int moma_attn_fwd(const float*
         const int64_t tot = (int64_t)H * N * N;
         launch_pdl(attn_probs_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, qkv, lse, n, c, H, scale, attn_probs);
     }
-    sgemm(o, C, 1, w_proj, C, 1, b_proj, y, C, n, c, c, st);
+    const bool fused_copy = y_bf16 != nullptr && !use_simt_gemm() && ldc_is_dense(C, c);
+    sgemm(o, C, 1, w_proj, C, 1, b_proj, y, C, n, c, c, st, fused_copy ? y_bf16 : nullptr);
+    if (y_bf16 != nullptr && !fused_copy) {
+        int rc2 = moma_cast_bf16(y, y_bf16, N * C, stream);
+        if (rc2 != MOMA_OK) return rc2;
+    }
     MOMA_CUDA_LAUNCH_CHECK("attn_fwd");
     note_launches(attn_probs ? 4 : 3);
     return MOMA_OK;

@@ -37,7 +37,7 @@ int gemm_splits(int M, int N, int K);
 size_t gemm_workspace_bytes(int M, int N, int K);
 int gemm_nt(const float* A, const float* a_mask, int64_t a_rs, int64_t a_cs, const float* Bm, int64_t b_rs, int64_t b_cs,
             const float* bias, float* C, int64_t ldc, int M, int N, int K, int relu, void* workspace, size_t workspace_bytes,
-            cudaStream_t st);
+            cudaStream_t st, void* c_bf16 = nullptr);     // c_bf16: optional dense [M, N] bf16 copy of C
 void colsum_masked(const float* X, const float* mask, int rows, int cols, float* out, cudaStream_t st);
 bool use_simt_gemm();        // MOMA_B200_GEMM=simt: IEEE-FP32 CUDA-core GEMMs instead (A/B switch, read once)
 

@@ -81,6 +81,7 @@ struct GemmParams {
     const float* a_mask;       // optional, indexed like A: elements with mask <= 0 read as 0 (ReLU backward)
     const float* bias;
     float* C;
+    __nv_bfloat16* C_bf16;     // optional second output: the same values rounded to bf16, dense [M, N]
     int64_t ldc;
     int M, N, K, relu, splits;
     float* partial;            // [splits, M, N] when splits > 1
@@ -173,6 +174,11 @@ gemm3xtf32_kernel(const GemmParams p) {
         float* dst = p.C + (int64_t)r * p.ldc + c;
         if (c + 1 < p.N && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
         else { if (c < p.N) dst[0] = v0; if (c + 1 < p.N) dst[1] = v1; }
+        if (p.C_bf16) {
+            __nv_bfloat16* d16 = p.C_bf16 + (int64_t)r * p.N + c;
+            if (c + 1 < p.N && ((reinterpret_cast<uintptr_t>(d16) & 3) == 0)) *reinterpret_cast<__nv_bfloat162*>(d16) = __floats2bfloat162_rn(v0, v1);
+            else { if (c < p.N) d16[0] = __float2bfloat16_rn(v0); if (c + 1 < p.N) d16[1] = __float2bfloat16_rn(v1); }
+        }
     };
     if (p.splits == 1) {
 #pragma unroll
@@ -297,11 +303,11 @@ size_t gemm_workspace_bytes(int M, int N, int K) {
 // ticket counters: they must be zero before the first use and are left zero by every launch.
 int gemm_nt(const float* A, const float* a_mask, int64_t a_rs, int64_t a_cs, const float* Bm, int64_t b_rs, int64_t b_cs,
             const float* bias, float* C, int64_t ldc, int M, int N, int K, int relu, void* workspace, size_t workspace_bytes,
-            cudaStream_t st) {
+            cudaStream_t st, void* c_bf16) {
     GemmParams p;
     p.a = Operand{A, a_rs, a_cs, M, operand_mode(A, a_mask, a_rs, a_cs, M, K)};
     p.b = Operand{Bm, b_rs, b_cs, N, operand_mode(Bm, nullptr, b_rs, b_cs, N, K)};
-    p.a_mask = a_mask; p.bias = bias; p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.relu = relu;
+    p.a_mask = a_mask; p.bias = bias; p.C = C; p.C_bf16 = static_cast<__nv_bfloat16*>(c_bf16); p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.relu = relu;
     p.splits = 1; p.partial = nullptr; p.tickets = nullptr;
     if (workspace != nullptr) {
         const int s = gemm_splits(M, N, K);

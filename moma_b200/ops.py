@@ -256,6 +256,9 @@ def nce_operands(q: torch.Tensor, k: torch.Tensor, precision: str):
     partial kernel reads a bf16 copy of q; the combine kernel rounds q / k inline (round_bf16)."""
     q32, k32 = _f32c(q.detach()), _f32c(k.detach())
     if precision == "bf16":
+        cached = getattr(q, "_moma_bf16", None)       # left by ops.attention when q is its (unmodified) output
+        if cached is not None and cached[1] == q._version and cached[0].shape == q32.shape and q.dtype == torch.float32:
+            return cached[0], BF16, q32, k32, True
         qb = torch.empty(q32.shape, dtype=torch.bfloat16, device=q32.device)
         cast_bf16(q32, qb)
         return qb, BF16, q32, k32, True
@@ -374,7 +377,7 @@ def nce_logits_qk(q, k, T) -> torch.Tensor:
 # -------------------------------------------------------------------------- attention
 class _Attention(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w_qkv, b_qkv, w_proj, b_proj, H, want_probs):
+    def forward(ctx, x, w_qkv, b_qkv, w_proj, b_proj, H, want_probs, want_bf16=False):
         lib = _lib.load()
         xc, wq, wp, bp = _f32c(x), _f32c(w_qkv), _f32c(w_proj), _f32c(b_proj)
         bq = _f32c(b_qkv) if b_qkv is not None else None
@@ -385,14 +388,18 @@ class _Attention(torch.autograd.Function):
         o = torch.empty((N, C), dtype=torch.float32, device=dev)
         lse = torch.empty((H, N), dtype=torch.float32, device=dev)
         probs = torch.empty((1, H, N, N), dtype=torch.float32, device=dev) if want_probs else None
+        y16 = torch.empty((N, C), dtype=torch.bfloat16, device=dev) if want_bf16 else None
         check(lib.moma_attn_fwd(_p(xc), _p(wq), _p(bq), _p(wp), _p(bp), N, C, H, _p(y), _p(qkv), _p(o), _p(lse),
-                                _p(probs), _stream()))
+                                _p(probs), _p(y16), _stream()))
         ctx.save_for_backward(xc, wq, wp, qkv, o, lse)
         ctx.H = H
         ctx.has_bq = b_qkv is not None
         if want_probs:
             ctx.mark_non_differentiable(probs)
             return y, probs
+        if want_bf16:
+            ctx.mark_non_differentiable(y16)
+            return y, y16
         return y
 
     @staticmethod
@@ -413,7 +420,7 @@ class _Attention(torch.autograd.Function):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         check(lib.moma_attn_bwd(_p(xc), _p(wq), _p(wp), _p(qkv), _p(o), _p(lse), _p(gy), N, C, H, _p(gx), _p(gwq),
                                 _p(gbq), _p(gwp), _p(gbp), _p(ws), ws_bytes, _stream()))
-        return gx, gwq, gbq, gwp, gbp, None, None
+        return gx, gwq, gbq, gwp, gbp, None, None, None
 
 
 def attention(x, w_qkv, b_qkv, w_proj, b_proj, num_heads: int, want_probs: bool = False):
@@ -421,6 +428,12 @@ def attention(x, w_qkv, b_qkv, w_proj, b_proj, num_heads: int, want_probs: bool 
     _need_cuda(x, w_qkv, w_proj)
     if x.dim() != 2:
         raise RuntimeError("moma_b200.attention: expects [N, C]")
+    if not want_probs and _PRECISION == "bf16" and bf16_supported(x.shape[1]):
+        # the projection's epilogue also emits y in bf16: if y becomes the query of the InfoNCE pass, its tensor-core
+        # operand is already there (nce_operands) and no cast kernel is launched
+        y, y16 = _Attention.apply(x, w_qkv, b_qkv, w_proj, b_proj, int(num_heads), False, True)
+        y._moma_bf16 = (y16, y._version)
+        return y
     return _Attention.apply(x, w_qkv, b_qkv, w_proj, b_proj, int(num_heads), bool(want_probs))
 
 

@@ -49,7 +49,7 @@ def test_version_and_error_string(lib):
     assert rc == -1 and b"duplicate ids" in lib.moma_last_error()
     rc = lib.moma_enqueue(16, 2, 8, 16, None, 9, 0, None, 0, 2, 0, 1e-12, None)   # K % world != 0
     assert rc == -1
-    rc = lib.moma_attn_fwd(16, 16, None, 16, 16, 8, 40, 4, 16, 16, 16, 16, None, None)   # head_dim 10
+    rc = lib.moma_attn_fwd(16, 16, None, 16, 16, 8, 40, 4, 16, 16, 16, 16, None, None, None)   # head_dim 10
     assert rc == -3 and b"head_dim" in lib.moma_last_error()
     rc = lib.moma_nce_partial(16, 16, 8, 1024, 64, 1.0, _lib.F32, 1, 16, 16, 16, 16, None)   # D > 512
     assert rc == -3

@@ -647,3 +647,45 @@ def test_deferred_enqueue_equals_inline():
         ce(lb, lbb).backward()
         b.enqueue(all_k)
         assert torch.equal(q1.grad, q2.grad) and torch.equal(a.memory, b.memory) and a.index == b.index
+
+
+@pytest.mark.gpu
+def test_attention_emits_the_bf16_query_operand():
+    """In bf16 mode the attention's output projection also writes y rounded to bf16 (moma_attn_fwd's y_bf16): it must be
+    bit-identical to the separate cast, be picked up by the InfoNCE pass, and be ignored once y was modified in place."""
+    import torch
+    import moma_b200
+    from moma_b200 import Attention, MoCo, ops
+    if not ops.bf16_supported(128):
+        pytest.skip("no tcgen05 path on this device")
+    moma_b200.set_precision("bf16")
+    try:
+        torch.manual_seed(11)
+        att = Attention(128, num_heads=4, qkv_bias=True).cuda()
+        x = torch.randn(96, 128, device="cuda", requires_grad=True)
+        y = att(x)
+        y16, ver = y._moma_bf16
+        assert ver == y._version and torch.equal(y16, y.detach().to(torch.bfloat16))
+        lib = ops._lib.load()
+        lib.moma_debug_launch_count(1)
+        q_op = ops.nce_operands(y, torch.randn(96, 128, device="cuda"), "bf16")[0]
+        assert q_op is y16 and int(lib.moma_debug_launch_count(0)) == 0           # no cast kernel
+        # the loss / gradient through the cached operand equal the ones through an explicit cast
+        torch.manual_seed(12)
+        a = MoCo(128, 1024, 0.15).cuda()
+        torch.manual_seed(12)
+        b = MoCo(128, 1024, 0.15).cuda()
+        k = torch.randn(96, 128, device="cuda")
+        ce = torch.nn.CrossEntropyLoss()
+        la, lab = a(y, k)
+        ga = torch.autograd.grad(ce(la, lab), x, retain_graph=True)[0]
+        y2 = y * 1.0                                                               # same values, no cached operand
+        assert getattr(y2, "_moma_bf16", None) is None
+        lb, lbb = b(y2, k)
+        gb = torch.autograd.grad(ce(lb, lbb), x)[0]
+        assert torch.equal(ga, gb)
+        with torch.no_grad():
+            y.mul_(2.0)                                                            # in-place change: cache is stale
+        assert ops.nce_operands(y, k, "bf16")[0] is not y16
+    finally:
+        moma_b200.set_precision("bf16")
