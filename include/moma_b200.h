@@ -234,7 +234,7 @@ int moma_linear_bwd(const float *x, const float *w, const float *y, const float 
  *     (stride 0: all-gather; stride = one block: all-to-all); with
  *     cast_f32_to_bf16 the source is fp32 and the pushed rows are bf16.
  *   out: [world, bytes_per_rank], slot s = the rows pushed by rank s.
- * A peer that never arrives traps the kernel after a bounded wait (no hang).
+ * A peer that never arrives traps the kernel after a bounded wait (~30 s; no hang).
  * ------------------------------------------------------------------------- */
 size_t moma_peer_ctrl_bytes(void);
 int moma_peer_exchange(const void *src, int64_t src_peer_stride_bytes, int64_t bytes_per_rank,

@@ -25,6 +25,9 @@ namespace moma {
 namespace {
 
 constexpr int kPeerMaxWorld = 16, kPeerChannels = 4, kPeerThreads = 256;
+// A peer may legitimately be late by a host-side hiccup (graph instantiation, allocator growth): wait ~30 s of SM clocks
+// before declaring it dead -- long enough for that, short enough that a lost rank becomes an error instead of a hang.
+constexpr long long kPeerTimeoutClk = 60000000000ll;
 
 struct PeerCtrl {
     unsigned long long epoch[kPeerChannels];
@@ -81,7 +84,7 @@ peer_exchange_kernel(const void* __restrict__ src, long long src_peer_stride_byt
     for (long long i = (long long)blockIdx.x * kPeerThreads + threadIdx.x; i < total; i += stride) {
         uint4 c = ld_volatile16(in + i);
         while (c.y != tag || c.w != tag) {
-            if (clock64() - t0 > 8000000000ll) { atomicExch(&g_peer_error, 1 + channel); __trap(); }
+            if (clock64() - t0 > kPeerTimeoutClk) { atomicExch(&g_peer_error, 1 + channel); __trap(); }
             c = ld_volatile16(in + i);
         }
         o2[i] = make_uint2(c.x, c.z);
