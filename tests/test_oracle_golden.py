@@ -212,3 +212,22 @@ def test_criterion_step_golden(golden):
         for n in list(sd):
             sd[n] = g[f"st{st}_sd_{n}"].copy()
     assert index == 48 % 40
+
+
+def test_linear_backward_matches_torch_autograd():
+    """oracle.linear / linear_backward (the heads' nn.Linear + nn.ReLU) against torch autograd in float64."""
+    import torch
+    rng = np.random.default_rng(3)
+    x, w, b = rng.standard_normal((9, 7)), rng.standard_normal((5, 7)), rng.standard_normal(5)
+    gy = rng.standard_normal((9, 5))
+    for relu in (False, True):
+        xt, wt, bt = (torch.tensor(a, requires_grad=True) for a in (x, w, b))
+        yt = torch.nn.functional.linear(xt, wt, bt)
+        yt = torch.relu(yt) if relu else yt
+        gx, gw, gb = torch.autograd.grad(yt, (xt, wt, bt), torch.tensor(gy))
+        y = O.linear(x, w, b)
+        y = np.maximum(y, 0) if relu else y
+        assert np.allclose(y, yt.detach().numpy(), rtol=1e-13, atol=1e-13)
+        ox, ow, ob = O.linear_backward(x, w, y, gy, relu=relu)
+        for got, want in ((ox, gx), (ow, gw), (ob, gb)):
+            assert np.allclose(got, want.numpy(), rtol=1e-12, atol=1e-12)
