@@ -598,6 +598,15 @@ def test_linear_matches_fp64_reference(M, N, K, relu, bias):
     assert rel(y.detach(), yd.detach()) < 2e-6
     for got, want in zip(grads, gd):
         assert rel(got, want) < 2e-6
+    # and against the numpy oracle (oracle/moma_oracle.py: linear / linear_backward) in float64
+    xo, wo = x.detach().double().cpu().numpy(), w.detach().double().cpu().numpy()
+    bo = b.detach().double().cpu().numpy() if bias else 0.0
+    yo = O.linear(xo, wo, bo)
+    yo = np.maximum(yo, 0) if relu else yo
+    assert np.linalg.norm(y.detach().cpu().numpy() - yo) < 2e-6 * np.linalg.norm(yo)
+    ox, ow, ob = O.linear_backward(xo, wo, y.detach().double().cpu().numpy(), gy.double().cpu().numpy(), relu=relu)
+    for got, want in zip(grads, (ox, ow, ob)):
+        assert np.linalg.norm(got.double().cpu().numpy() - want) < 2e-6 * max(np.linalg.norm(want), 1e-30)
 
 
 @pytest.mark.gpu
