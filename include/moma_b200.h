@@ -10,7 +10,13 @@
  *   - every buffer (inputs, outputs, workspaces, the queue and its bf16 shadow)
  *     is allocated and owned by the caller; the library never allocates or frees
  *     device memory and keeps no pointer past the call.
- *   - all work is enqueued asynchronously on `stream`; no device sync inside.
+ *   - all work is enqueued asynchronously on `stream`; no device sync inside.  The
+ *     backward entry points (moma_attn_bwd, moma_linear_bwd) fork independent
+ *     kernels onto library-owned side streams and join them back into `stream`
+ *     with events before returning (parallel branches under graph capture).
+ *   - kernels are launched with programmatic stream serialization (PDL): each
+ *     waits for its predecessor in `stream` before its first global access, so
+ *     the ordering a caller observes is plain stream order.
  *   - return value: MOMA_OK (0) or a negative moma_status; moma_last_error()
  *     returns a thread-local message for the last failure on this thread.
  *   - row-major, fp32 unless a `dtype` argument says otherwise; 16-byte aligned
