@@ -88,7 +88,40 @@ struct GemmParams {
     unsigned int* tickets;     // one per output tile, zero between launches
 };
 
-template <bool MASK>
+// Per-thread state of one operand's tile copies in the two vector modes: everything that does not change from slab to
+// slab (source offset, shared-memory offset, the row bound) is computed once, so a slab costs two pointer adds, two
+// compares and two cp.async per operand instead of re-deriving 64-bit addresses through the mode dispatch.
+struct TileLoader {
+    long long off[2];      // element offset of this thread's two 16-byte vectors at slab 0
+    long long kstep;       // element offset between consecutive slabs
+    int dst[2];            // float offset inside the shared-memory tile
+    int kidx[2];           // k index (inside the slab) of the vector's first element
+    bool ok[2];            // row bound (static)
+};
+__device__ __forceinline__ void loader_init(TileLoader& L, const Operand& op, int row0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int idx = threadIdx.x + i * kThreads, o = idx >> 3, v = (idx & 7) * 4;
+        if (op.mode == kVecK) {          // outer = row, vector along k
+            L.ok[i] = row0 + o < op.rows; L.kidx[i] = v; L.dst[i] = o * kLdK + v;
+            L.off[i] = (long long)(row0 + o) * op.rs + v;
+        } else {                          // kVecR: outer = k, vector along the rows
+            L.ok[i] = row0 + v < op.rows; L.kidx[i] = o; L.dst[i] = o * kLdR + v;
+            L.off[i] = (long long)o * op.cs + row0 + v;
+        }
+    }
+    L.kstep = op.mode == kVecK ? (long long)kTK : (long long)kTK * op.cs;
+}
+__device__ __forceinline__ void loader_issue(const TileLoader& L, float* tile, const float* __restrict__ base, int kt, int K) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const bool ok = L.ok[i] && kt * kTK + L.kidx[i] < K;
+        cp_async16(tile + L.dst[i], ok ? base + L.off[i] + kt * L.kstep : base, ok);
+    }
+}
+
+// SCALAR: at least one operand needs element-wise copies (odd shapes / unaligned views): generic, slower addressing
+template <bool MASK, bool SCALAR>
 __global__ void __launch_bounds__(kThreads)
 gemm3xtf32_kernel(const GemmParams p) {
     __shared__ __align__(16) float sA[kStages][kTile];
@@ -109,10 +142,18 @@ gemm3xtf32_kernel(const GemmParams p) {
     const int b_base = (wn + g) * b_sr + t * b_sk;
 
     pdl_wait();                     // operands may come from the kernel launched just before this one
+    TileLoader la, lb;
+    if (!SCALAR) { loader_init(la, p.a, m0); loader_init(lb, p.b, n0); }
     auto issue = [&](int stage, int kt) {
-        issue_tile(sA[stage], p.a.p, p.a, m0, kt * kTK, p.K);
-        issue_tile(sB[stage], p.b.p, p.b, n0, kt * kTK, p.K);
-        if (MASK) issue_tile(sM[stage], p.a_mask, p.a, m0, kt * kTK, p.K);
+        if (SCALAR) {
+            issue_tile(sA[stage], p.a.p, p.a, m0, kt * kTK, p.K);
+            issue_tile(sB[stage], p.b.p, p.b, n0, kt * kTK, p.K);
+            if (MASK) issue_tile(sM[stage], p.a_mask, p.a, m0, kt * kTK, p.K);
+        } else {
+            loader_issue(la, sA[stage], p.a.p, kt, p.K);
+            loader_issue(lb, sB[stage], p.b.p, kt, p.K);
+            if (MASK) loader_issue(la, sM[stage], p.a_mask, kt, p.K);
+        }
     };
 #pragma unroll
     for (int s = 0; s < kStages - 1; ++s) {
@@ -321,8 +362,14 @@ int gemm_nt(const float* A, const float* a_mask, int64_t a_rs, int64_t a_cs, con
         }
     }
     const dim3 grid((N + kTN - 1) / kTN, (M + kTM - 1) / kTM, p.splits);
-    if (a_mask) launch_pdl(gemm3xtf32_kernel<true>, grid, dim3(kThreads), 0, st, p);
-    else launch_pdl(gemm3xtf32_kernel<false>, grid, dim3(kThreads), 0, st, p);
+    const bool scalar = p.a.mode == kScalar || p.b.mode == kScalar;
+    if (scalar) {
+        if (a_mask) launch_pdl(gemm3xtf32_kernel<true, true>, grid, dim3(kThreads), 0, st, p);
+        else launch_pdl(gemm3xtf32_kernel<false, true>, grid, dim3(kThreads), 0, st, p);
+    } else {
+        if (a_mask) launch_pdl(gemm3xtf32_kernel<true, false>, grid, dim3(kThreads), 0, st, p);
+        else launch_pdl(gemm3xtf32_kernel<false, false>, grid, dim3(kThreads), 0, st, p);
+    }
     MOMA_CUDA_LAUNCH_CHECK("gemm3xtf32");
     return MOMA_OK;
 }
