@@ -62,18 +62,23 @@ peer_exchange_kernel(const void* __restrict__ src, long long src_peer_stride_byt
     const long long total = pairs_per_rank * world;
     const long long stride = (long long)gridDim.x * kPeerThreads;
 
-    // ---- push: (peer p, pair v) -> cell v of slot `rank` in p's region
-    for (long long i = (long long)blockIdx.x * kPeerThreads + threadIdx.x; i < total; i += stride) {
-        const int p = (int)(i / pairs_per_rank);
-        const long long v = i - (long long)p * pairs_per_rank;
-        uint2 w;
-        if (CAST) {
-            const float4 f = *(reinterpret_cast<const float4*>(static_cast<const char*>(src) + p * src_peer_stride_bytes) + v);
-            w = make_uint2(pack2(f.x, f.y), pack2(f.z, f.w));
-        } else {
-            w = *(reinterpret_cast<const uint2*>(static_cast<const char*>(src) + p * src_peer_stride_bytes) + v);
+    // ---- push: pair v of this rank's rows for peer p -> cell v of slot `rank` in p's region.  The pair index is the
+    // outer loop (no integer division per element); for an all-gather (stride 0) the source is read once for all peers.
+    const long long slot = region + (long long)rank * pairs_per_rank * 16;
+    for (long long v = (long long)blockIdx.x * kPeerThreads + threadIdx.x; v < pairs_per_rank; v += stride) {
+        uint2 w = make_uint2(0u, 0u);
+        for (int p = 0; p < world; ++p) {
+            if (p == 0 || src_peer_stride_bytes != 0) {
+                const char* s = static_cast<const char*>(src) + (long long)p * src_peer_stride_bytes;
+                if (CAST) {
+                    const float4 f = *(reinterpret_cast<const float4*>(s) + v);
+                    w = make_uint2(pack2(f.x, f.y), pack2(f.z, f.w));
+                } else {
+                    w = *(reinterpret_cast<const uint2*>(s) + v);
+                }
+            }
+            *reinterpret_cast<uint4*>(peer_bases[p] + slot + v * 16) = make_uint4(w.x, tag, w.y, tag);
         }
-        *reinterpret_cast<uint4*>(peer_bases[p] + region + ((long long)rank * pairs_per_rank + v) * 16) = make_uint4(w.x, tag, w.y, tag);
     }
     pdl_launch_dependents();
 

@@ -5,7 +5,7 @@
 
 Every rank holds a replicated MoCo (the reference's layout) and a ShardedMoCo with the same initial
 queue; each step both see the same local (q, k) and the same all-gathered keys.  Loss rows, dq and
-the top-1 flags must agree (fp32: 1e-5; bf16: 1e-3) and the gathered shards must equal the
+the top-1 flags must agree (fp32: 1e-5; bf16: 2e-3 between the two layouts, each 1e-3 from the oracle) and the gathered shards must equal the
 replicated queue bit-exactly after every step.
 """
 import os
@@ -62,7 +62,10 @@ def main():
     check_peer(rank, world)
     ce = torch.nn.CrossEntropyLoss()
     worst = {}
-    for precision, tol in (("fp32", 1e-5), ("bf16", 1e-3)):
+    # bf16: both layouts are separately within 1e-3 of the oracle (tests/test_parity_gpu.py; measured 1e-4 on normalised
+    # inputs, scripts/nce_bf16_error.py); two such results may differ by the sum of their errors, and the un-normalised
+    # queries used here (|q| ~ 7, logits up to +-140 at T = 0.07) are the worst case for the bf16 rounding of P
+    for precision, tol in (("fp32", 1e-5), ("bf16", 2e-3)):
         moma_b200.set_precision(precision)
         for (B, D, K, T) in ((64, 128, 4096, 0.15), (128, 256, 8192, 0.07), (32, 64, 1024, 0.15)):
             torch.manual_seed(7)
