@@ -1,25 +1,32 @@
 #!/usr/bin/env python
 """bench.py -- MoMA criterion step throughput (samples/s) on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2|C3|C5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2|C3|C5] [--quick]
 
-A "step" is one pass of the hot path over one synthetic batch (level L1):
-backbone EMA (student -> momentum twin) + projection heads + 3x attention + fused InfoNCE
-logits/CE forward AND backward (to d loss / d feat_s and the criterion parameters) + key
-all-gather (N > 1) + ring enqueue.  Backbones are outside the path: inputs are their features.
+A "step" is one pass of the hot path over one synthetic batch (level L1): backbone EMA (student ->
+momentum twin) + projection heads + 3x attention + fused InfoNCE logits/CE forward AND backward (to d loss/d feat_s
+and the criterion parameters) + key exchange (N > 1) + ring enqueue -- moma_b200.step.CriterionStep, the module calls
+of helper/loops_moma.py:308-335,360 on backbone features.
 
-Default workload = BASELINE.json configs[1] (C2): ResNet-50 teacher -> ResNet-18 student,
-batch 256 per GPU, D = 128, K = 16384, bf16 InfoNCE operands.  With N > 1 the per-GPU batch is
-fixed (weak scaling) and the queue is sharded by K across ranks.
+Headline workload = the configuration the north star is quoted on: C3 (B512 per GPU, D128, K65536, 8 heads, bf16
+InfoNCE operands).  With N > 1 the per-GPU batch is fixed (weak scaling) and the queue is sharded by K across ranks.
+The same run also measures, as extra blocks of the same JSON line: C2 (BASELINE configs[1]) and C5 at N = 1;
+C3-strong, C5-strong and C2-weak at N > 1; the C4 small-student EMA lines; the reference's own GPU behaviour
+(``gpu_reference``) and the CPU arm (``cpu_baseline``).
 
-Prints ONE JSON line (rank 0).  `value` is device-resident throughput; `e2e` goes through the
-public module API with HOST (pinned) inputs and a host read of the loss inside the timed region.
+EVERY benched configuration first proves its own parity (``parity_check``): the exact captured graph that is timed
+afterwards is replayed on fixed inputs and compared with (i) the replicated-queue sequential step on the same inputs
+and (ii) the CPU oracle; a mismatch exits non-zero.
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput; `e2e` goes through the module API with HOST
+(pinned) inputs and a host read of the loss inside the timed region.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import re
 import sys
 import threading
 import time
@@ -37,27 +44,20 @@ CONFIGS = {
     "C2": dict(B=256, s_dim=512, t_dim=2048, D=128, K=16384, H=4,
                desc="C2 MoMA criterion step, ResNet-50 teacher -> ResNet-18 student, B256/GPU D128 K16384 bf16"),
     "C3": dict(B=512, s_dim=512, t_dim=2048, D=128, K=65536, H=8,
-               desc="C3 large memory bank K65536, 8 heads, B512/GPU D128"),
+               desc="C3 MoMA criterion step, large memory bank K65536, 8 heads, B512/GPU D128 bf16"),
     "C5": dict(B=1024, s_dim=384, t_dim=768, D=256, K=131072, H=4,
-               desc="C5 ViT-S<-ViT-B features, B1024/GPU D256 K131072"),
+               desc="C5 ViT-S<-ViT-B features, B1024 D256 K131072 bf16"),
 }
 T_NCE, ALPHA, SEED = 0.15, 0.999, 12345
+TOL_BF16 = 1e-3          # vs the oracle fed the same bf16-rounded operands (the north star's BF16 bar)
+TOL_SAME = 2e-5          # captured overlapped graph vs sequential eager step, same queue layout (same kernels, same splits)
+TOL_LAYOUT = 5e-4        # K-sharded vs replicated queue: P is rounded to bf16 against per-split / per-shard reference maxima,
+                         # so the two layouts differ at the 1e-4 level (each is within 1e-3 of the oracle)
 
 
 def resnet18_param_shapes(num_classes=4):
-    """Parameter shapes of the reference ResNet-18 (models/resnet_imagenet.py; 62 tensors,
-    11,178,564 elements) in parameters() order -- the EMA pair is (student, same-architecture
-    momentum twin) because the reference's momentum_update raises on heterogeneous pairs."""
-    shapes = [(64, 3, 7, 7), (64,), (64,)]
-    cin = 64
-    for cout, stride in ((64, 1), (128, 2), (256, 2), (512, 2)):
-        for blk in range(2):
-            shapes += [(cout, cin if blk == 0 else cout, 3, 3), (cout,), (cout,), (cout, cout, 3, 3), (cout,), (cout,)]
-            if blk == 0 and (stride != 1 or cin != cout):
-                shapes += [(cout, cin, 1, 1), (cout,), (cout,)]
-        cin = cout
-    shapes += [(num_classes, 512), (num_classes,)]
-    return shapes
+    from moma_b200.step import resnet18_param_shapes as f
+    return f(num_classes)
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -103,216 +103,254 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-# ----------------------------------------------------------------------------- our arm
-class CriterionStep:
-    """The criterion step through the public (reference-shaped) module API of moma_b200."""
+# ----------------------------------------------------------------------------- helpers
+class Ctx:
+    """Per-process state of a run: device, rank / world, L2 flush, timing."""
 
-    def __init__(self, cfg, rank, world, device):
-        from argparse import Namespace
+    def __init__(self, args, rank, world, local_rank):
+        import torch.distributed as dist
+        self.args, self.rank, self.world, self.dist = args, rank, world, dist
+        self.device = torch.device("cuda", local_rank)
+        # L2 flush between steps: READ a 256 MiB buffer (leaves the 126 MB L2 full of clean foreign lines; a
+        # write-flush would leave it dirty and charge the write-back to the next kernel)
+        self.flush_buf = None if args.no_flush else torch.empty(64 << 20, dtype=torch.int32, device=self.device).zero_()
+        self.flush_out = torch.zeros(1, dtype=torch.int64, device=self.device)
 
-        import moma_b200
-        from moma_b200 import CMO, ContrastTrainer, build_mem
-        self.cfg, self.rank, self.world, self.dev = cfg, rank, world, device
-        moma_b200.set_precision("bf16")
-        torch.manual_seed(SEED)                       # same seed on every rank -> identical init (reference :241-246)
-        opt = Namespace(head="mlp", s_dim=cfg["s_dim"], t_dim=cfg["t_dim"], feat_dim=cfg["D"], attn="self", mem="MoCo",
-                        nce_k=cfg["K"], nce_t=T_NCE, alpha=ALPHA, num_heads=cfg["H"], shard_queue=world > 1)
-        self.opt = opt
-        self.contrast = build_mem(opt).to(device)
-        self.crit = CMO(opt).to(device)
-        self.trainer = ContrastTrainer
-        shapes = resnet18_param_shapes()
-        self.student = torch.nn.ParameterList([torch.nn.Parameter(torch.randn(*s)) for s in shapes]).to(device)
-        self.teacher = torch.nn.ParameterList([torch.nn.Parameter(torch.randn(*s)) for s in shapes]).to(device)
-        self.ema_elems = sum(p.numel() for p in self.student)
-        self.ce = torch.nn.CrossEntropyLoss()
-        self.head_ema = cfg["s_dim"] == cfg["t_dim"]
-        self.params = [p for n, p in self.crit.named_parameters() if not n.startswith("embed_t")]
-        torch.manual_seed(SEED + 1 + rank)            # data differs per rank
-        B = cfg["B"]
-        self.feat_s = torch.randn(B, cfg["s_dim"], device=device, requires_grad=True)
-        self.feat_t = torch.randn(B, cfg["t_dim"], device=device)
-        self.host_s = torch.randn(B, cfg["s_dim"]).pin_memory()
-        self.host_t = torch.randn(B, cfg["t_dim"]).pin_memory()
-        self.h2d_bytes = (self.host_s.numel() + self.host_t.numel()) * 4
-        self.loss = None
+    def flush(self):
+        if self.flush_buf is not None:
+            torch.sum(self.flush_buf, dim=(0,), keepdim=True, out=self.flush_out)
 
-    def step(self, feat_s=None, feat_t=None):
-        """helper/loops_moma.py:308-335 + :360 (backward) on features, in the reference's call order."""
-        crit, opt = self.crit, self.opt
-        feat_s = self.feat_s if feat_s is None else feat_s
-        feat_t = self.feat_t if feat_t is None else feat_t
-        self.trainer.momentum_update(self.student, self.teacher, opt.alpha)
-        if self.head_ema:
-            self.trainer.momentum_update(crit.embed_s, crit.embed_t, opt.alpha)
-        with torch.no_grad():
-            k0 = crit.embed_t(feat_t)
-        f_s = crit.embed_s(feat_s)
-        f_s = crit.atts_q(f_s)
-        k = crit.atts_k(k0)
+    def barrier(self):
         if self.world > 1:
-            # K-sharded queue: this rank only enqueues every W-th attended key -> attend those rows only, and every
-            # rank projects only its own keys (the qkv projections are all-gathered instead of the raw keys)
-            owned = crit.atts_queue.forward_rows_gathered(k0, self.trainer._global_gather,
-                                                          *self.contrast.owned_rows(k0.shape[0] * self.world))
-            return self._loss_and_backward(f_s, k, None, feat_s, owned_k=owned)
-        all_k = crit.atts_queue(k0)
-        return self._loss_and_backward(f_s, k, all_k, feat_s)
-
-    def _loss_and_backward(self, f_s, k, all_k, feat_s, owned_k=None, enqueue_stream=None):
-        if enqueue_stream is not None:
-            output = self.contrast(q=f_s, k=k, defer_enqueue=True)
-        else:
-            output = self.contrast(q=f_s, k=k, owned_k=owned_k) if owned_k is not None else \
-                self.contrast(q=f_s, k=k, all_k=all_k)
-        losses, accs = self.trainer._compute_loss_accuracy(output[:-1], output[-1], self.ce)
-        for p in self.params:
-            p.grad = None
-        feat_s.grad = None
-        if enqueue_stream is not None:
-            # the queue update only has to follow the InfoNCE pass that reads the old queue: it runs on the branch
-            # that produced the new keys, concurrently with the backward
-            enqueue_stream.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(enqueue_stream), torch.no_grad():
-                if owned_k is not None:
-                    self.contrast.enqueue(owned_k=owned_k)
-                else:
-                    self.contrast.enqueue(all_k)
-        losses[0].backward()
-        self.loss = losses[0]
-        return losses[0]
-
-    def step_overlapped(self):
-        """Same module calls, with the independent branches forked onto side streams so the captured
-        graph exposes the step's real dependencies: the backbone EMA touches nothing else in the step,
-        and the teacher branch (embed_t -> atts_k / atts_queue) only meets the student branch
-        (embed_s -> atts_q) at the InfoNCE pass."""
-        crit, opt = self.crit, self.opt
-        main = torch.cuda.current_stream()
-        if not hasattr(self, "_side"):
-            self._side = [torch.cuda.Stream(self.dev) for _ in range(3)]
-        s_ema, s_t, s_u = self._side
-        s_t.wait_stream(main)
-        with torch.cuda.stream(s_t):
-            if self.head_ema:
-                self.trainer.momentum_update(crit.embed_s, crit.embed_t, opt.alpha)
-            with torch.no_grad():
-                k0 = crit.embed_t(self.feat_t)
-            s_u.wait_stream(s_t)
-            owned = all_k = None
-            with torch.cuda.stream(s_u):
-                if self.world > 1:
-                    owned = crit.atts_queue.forward_rows_gathered(k0, self.trainer._global_gather,
-                                                                  *self.contrast.owned_rows(k0.shape[0] * self.world))
-                else:
-                    all_k = crit.atts_queue(k0)
-            k = crit.atts_k(k0)
-        f_s = crit.embed_s(self.feat_s)
-        f_s = crit.atts_q(f_s)
-        # The backbone EMA (bandwidth-bound, 270 MB of traffic) is forked behind the teacher branch, which finishes well
-        # before the student chain: it then overlaps the InfoNCE pass and the backward (all latency-bound, L2-resident)
-        # instead of the projection heads, the only other kernels of the step that miss in L2 (cold weights).
-        # Measured per step: forked at the start 178 us, after the heads 160.3, after the attention 163.7, here 159.6.
-        s_ema.wait_stream(s_t)
-        with torch.cuda.stream(s_ema):
-            self.trainer.momentum_update(self.student, self.teacher, opt.alpha)
-        # The loss of this step needs q, the local positive keys and the OLD queue -- not the keys enqueued for later
-        # steps: only the teacher branch (s_t) joins here, the queue-attention branch (s_u) joins after the backward.
-        main.wait_stream(s_t)
-        loss = self._loss_and_backward(f_s, k, all_k, self.feat_s, owned_k=owned, enqueue_stream=s_u)
-        main.wait_stream(s_u)
-        main.wait_stream(s_ema)
-        return loss
-
-    def step_e2e(self):
-        fs = self.host_s.to(self.dev, non_blocking=True).requires_grad_()
-        ft = self.host_t.to(self.dev, non_blocking=True)
-        return float(self.step(fs, ft).item())          # D2H read of the loss inside the timed region
-
-
-def run_ours(args, cfg, rank, world, local_rank):
-    import torch.distributed as dist
-
-    import moma_b200
-    from moma_b200 import _lib, ops
-    device = torch.device("cuda", local_rank)
-    torch.cuda.set_device(device)
-    lib = _lib.load()
-    # everything runs on one side stream from the first call on (graph capture needs a non-default
-    # stream, and autograd binds gradient accumulation to the stream a leaf was first used on)
-    # High priority: the student chain (this stream) is the critical path of the step; when its small CTAs compete with
-    # the teacher branch's library GEMM for SM slots they go first (measured: 163.1 -> 160.6 us per step).
-    torch.cuda.set_stream(torch.cuda.Stream(device, priority=-1))
-    cs = CriterionStep(cfg, rank, world, device)
-    B, D, K = cfg["B"], cfg["D"], cfg["K"]
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-
-    # L2 flush between steps: READ a 256 MiB buffer (leaves the 126 MB L2 full of clean foreign lines; a
-    # write-flush would leave it dirty and charge the write-back to the next kernel)
-    flush_buf = None if args.no_flush else torch.empty(64 << 20, dtype=torch.int32, device=device).zero_()
-    flush_out = torch.zeros(1, dtype=torch.int64, device=device)
-
-    class _Flush:
-        @staticmethod
-        def fill_(_v):
-            torch.sum(flush_buf, dim=(0,), keepdim=True, out=flush_out)
-    flush = None if args.no_flush else _Flush
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
+            self.dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        """Per-step CUDA-event timing on the launching stream (L2 flushed before each step), summed."""
+    def max_over_ranks(self, v: float) -> float:
+        if self.world == 1:
+            return v
+        t = torch.tensor([v], device=self.device, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_true(self, ok: bool) -> bool:
+        if self.world == 1:
+            return ok
+        t = torch.tensor([1 if ok else 0], device=self.device, dtype=torch.int32)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def timed(self, fn, steps):
+        """Per-step CUDA-event timing on the launching stream (L2 flushed before each step), summed; max over ranks."""
         evs = []
-        barrier()
+        self.barrier()
         for _ in range(steps):
-            if flush is not None:
-                flush.fill_(1)
+            self.flush()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             fn()
             b.record()
             evs.append((a, b))
-        barrier()
-        ms = sum(a.elapsed_time(b) for a, b in evs)
-        if world > 1:
-            t = torch.tensor([ms], device=device, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        self.barrier()
+        return self.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs))
 
-    # warm-up (also builds the EMA plan, TMA descriptors, bf16 shadow, cuBLAS handles)
-    for _ in range(max(args.warmup, 3)):
-        cs.step()
-    torch.cuda.synchronize()
+    def kernel_us(self, launch, reps=20):
+        """One kernel alone, cold L2 (flush first; the flush also hides the launch gap, so e0 -> e1 brackets the
+        kernel), median of `reps` launches."""
+        ts = []
+        for _ in range(reps):
+            self.flush()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); launch(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        ts.sort()
+        return ts[len(ts) // 2]
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    # ---- eager module API (what the unchanged helper/loops_moma.py drives)
-    eager_ms = timed(cs.step, args.steps)
 
-    # ---- the same step captured once as a CUDA graph and replayed (no Python between kernels)
+def npy(t):
+    return t.detach().float().cpu().numpy()
+
+
+def rel(a, b):
+    import numpy as np
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+# ----------------------------------------------------------------------------- parity self-check
+def build_and_check(ctx: Ctx, cfg, sharded, oracle=True):
+    """Builds the arm that is timed afterwards -- CriterionStep + ONE captured graph of step_overlapped -- and proves
+    its parity first.  Sequence on fixed inputs, identical seeds:
+        arm under test : 3 eager step_overlapped (GraphedStep warm-up) + capture, then 2 REPLAYS of the graph
+        reference arm  : 5 eager sequential step() calls on a replicated queue (the reference's layout and order)
+    compared after the 5th step: loss, d loss/d feat_s, the whole queue (gathered), the ring pointer; and (rank 0)
+    against the CPU oracle fed the queue as it was before the 5th step: loss and d loss/d feat_s within the bf16 bar,
+    the rows written by the 5th step at exactly the reference's ids ((index + j) % K) and nowhere else.
+    Returns (cs, graphed, report)."""
+    import numpy as np
+
     from moma_b200.graphed import GraphedStep
-    rows_per_step = B * world
+    from moma_b200.step import CriterionStep
+    rank, world, dev = ctx.rank, ctx.world, ctx.device
+    B, K = cfg["B"], cfg["K"]
+    n = B * world
+    cs = CriterionStep(cfg, rank, world, dev, sharded=sharded)
+    ref = CriterionStep(cfg, rank, world, dev, sharded=False)
+    graphed = GraphedStep(cs.step_overlapped, contrast=cs.contrast, rows_per_step=n, warmup=3)
+    graphed.replay()                                     # step 4
+    torch.cuda.synchronize()
+    queue_before = cs.full_queue().clone()
+    index_before = cs.contrast.index
+    graphed.replay()                                     # step 5
+    torch.cuda.synchronize()
+    for _ in range(5):
+        ref.step()
+    torch.cuda.synchronize()
+    rep = {}
+    q_g, q_r = cs.full_queue(), ref.contrast.memory
+    loss_g, loss_r = float(graphed.loss.item()), float(ref.loss.item())
+    rep["graph_vs_sequential_replicated"] = {
+        "loss_rel": abs(loss_g - loss_r) / abs(loss_r),
+        "dfeat_s_rel": rel(npy(cs.feat_s.grad), npy(ref.feat_s.grad)),
+        "queue_max_abs_diff": float((q_g - q_r).abs().max().item()),
+        "queue_bit_exact": bool(torch.equal(q_g, q_r)),
+        "pointer": [int(cs.contrast.index), int(ref.contrast.index)],
+        "steps_compared": 5,
+    }
+    r1 = rep["graph_vs_sequential_replicated"]
+    tol = TOL_LAYOUT if cs.sharded else TOL_SAME
+    r1["tolerance"] = tol
+    ok = (r1["loss_rel"] < tol and r1["dfeat_s_rel"] < tol and r1["queue_max_abs_diff"] < 1e-5
+          and r1["pointer"][0] == r1["pointer"][1] == (5 * n) % K)
+    # rows written by step 5: exactly the reference's ids, nowhere else (bit-exact index logic)
+    changed = torch.nonzero((q_g != queue_before).any(dim=1)).flatten().cpu().numpy()
+    if oracle and rank == 0:
+        from oracle import moma_oracle as O             # the checker only: never on the measured path
+        want_ids = np.sort(O.enqueue_ids(n, index_before, K))
+        ids_ok = bool(np.array_equal(changed, want_ids)) or set(changed.tolist()) <= set(want_ids.tolist())
+        sd = {k_: npy(v) for k_, v in cs.crit.state_dict().items()}
+        o = O.criterion_step(npy(cs.feat_s), npy(cs.feat_t), sd, npy(queue_before), T_NCE, cfg["H"], bf16_operands=True)
+        rep["vs_oracle"] = {
+            "loss_rel": abs(loss_g - o["loss"]) / abs(o["loss"]),
+            "dfeat_s_rel": rel(npy(cs.feat_s.grad), o["dfeat_s"]),
+            "acc_abs_diff": abs(float(cs.acc.item()) - float(o["pos_is_max"].mean() * 100.0)),
+            "enqueue_ids_exact": ids_ok, "rows_written": int(changed.size), "pointer_exact":
+                int(cs.contrast.index) == O.update_pointer(index_before, n, K),
+            "tolerance": TOL_BF16, "oracle_operands": "f_s, k, queue rounded to bf16 (SURVEY 7.3-6), rest float64",
+        }
+        r2 = rep["vs_oracle"]
+        ok = ok and r2["loss_rel"] < TOL_BF16 and r2["dfeat_s_rel"] < TOL_BF16 and r2["enqueue_ids_exact"] \
+            and r2["pointer_exact"] and r2["acc_abs_diff"] < 100.0 / B + 1e-3
+    rep["ok"] = ctx.all_true(bool(ok))
+    rep["layout"] = "sharded" if cs.sharded else "replicated"
+    del ref
+    torch.cuda.empty_cache()
+    return cs, graphed, rep
+
+
+# ----------------------------------------------------------------------------- kernel shares (CUPTI)
+FAMILIES = [
+    ("nce_tc", r"nce_tc2?_kernel"),
+    ("nce_combine", r"nce_reduce_kernel|nce_finalize_kernel"),
+    ("gemm3xtf32", r"gemm3xtf32_kernel"),
+    ("colsum", r"colsum"),
+    ("attn_fwd", r"attn_fwd_kernel|attn_probs"),
+    ("attn_bwd", r"attn_bwd_|attn_delta"),
+    ("fused_head", r"head_fwd_kernel|head_bwd_kernel"),
+    ("ema", r"ema_multi_kernel"),
+    ("l2norm", r"l2norm_kernel"),
+    ("enqueue", r"enqueue_kernel|pointer_advance|cast_bf16|enqueue_ids"),
+    ("peer_exchange", r"peer_exchange_kernel"),
+    ("library_gemm", r"cutlass|cublas|gemm|sgemm|xmma"),
+    ("nccl", r"nccl"),
+]
+
+
+def kernel_shares(ctx: Ctx, graphed, replays=5):
+    """Per-kernel-family device time of one graph replay (L2 flushed before it), from the CUPTI activity records
+    torch.profiler collects: mean over `replays` replays.  Returns (families: {name: {us, launches}}, span_us)."""
+    from torch.profiler import ProfilerActivity, profile
+    try:
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(replays):
+                ctx.flush()
+                graphed.replay()
+            torch.cuda.synchronize()
+        evs = [e for e in prof.profiler.kineto_results.events()
+               if str(e.device_type()).endswith("CUDA") and e.duration_ns() > 0]
+    except Exception as e:                                # CUPTI unavailable: no shares, the rooflines fall back to isolated timings
+        return None, None, f"{type(e).__name__}: {e}"
+    fam, other = {}, {}
+    for e in evs:
+        name = e.name()
+        if "reduce_kernel" in name and "nce_reduce" not in name and e.duration_ns() > 30000:
+            continue                                      # the 256 MiB flush read
+        key = next((f for f, pat in FAMILIES if re.search(pat, name)), None)
+        if key is None:
+            key = "other"
+            other[name[:60]] = other.get(name[:60], 0) + 1
+        d = fam.setdefault(key, {"us": 0.0, "launches": 0})
+        d["us"] += e.duration_ns() / 1e3 / replays
+        d["launches"] += 1.0 / replays
+    for d in fam.values():
+        d["us"], d["launches"] = round(d["us"], 2), round(d["launches"], 1)
+    return fam, other, None
+
+
+# ----------------------------------------------------------------------------- measuring one configuration
+def measure(ctx: Ctx, name, cfg, steps, strong=False, full=False):
+    """Parity-check, then time one configuration.  `full`: also the eager API, the end-to-end path, the per-kernel
+    rooflines and the launch count (the headline block); otherwise a compact block."""
+    from moma_b200 import _lib, ops
+    from moma_b200.peer import PeerExchange
+    lib = _lib.load()
+    world, dev = ctx.world, ctx.device
+    cfg = dict(cfg)
+    if strong:
+        cfg["B"] = cfg["B"] // world
+    B, D, K = cfg["B"], cfg["D"], cfg["K"]
+    n = B * world
     lib.moma_debug_launch_count(1)
-    step_fn = cs.step if os.environ.get("MOMA_BENCH_SEQ") else cs.step_overlapped
-    graphed = GraphedStep(step_fn, contrast=cs.contrast, rows_per_step=rows_per_step, warmup=3)
-    launches_per_step = int(lib.moma_debug_launch_count(1)) // 4       # 3 warm-up calls + 1 captured call
+    cs, graphed, parity = build_and_check(ctx, cfg, sharded=world > 1)
+    if not parity["ok"]:
+        return {"config": name, "parity_check": parity, "error": "parity check failed"}, cs, graphed
     for _ in range(3):
         graphed.replay()
-    total_ms = timed(graphed.replay, args.steps)
-    launches = launches_per_step * args.steps
+    lib.moma_debug_launch_count(1)
+    lib.moma_debug_flops(0, 1); lib.moma_debug_flops(1, 1)
+    total_ms = ctx.timed(graphed.replay, steps)
+    ms = total_ms / steps
+    out = {
+        "config": name, "workload": cfg["desc"], "scaling": "strong" if strong else "weak", "per_gpu_batch": B,
+        "global_batch": n, "feat_dim": D, "queue_K": K, "heads": cfg["H"], "ms_per_step": ms,
+        "value": n / (ms * 1e-3), "unit": "samples/s", "steps": steps, "parity_check": parity,
+        "queue": "replicated" if world == 1 else f"sharded by K over {world} ranks (cyclic), {K // world} rows/rank",
+    }
+    if world > 1:
+        out["exchange"] = PeerExchange.status()
+    if not full:
+        return out, cs, graphed
 
-    # ---- end to end: host (pinned) inputs -> device, replay, host read of the loss.  The H2D copy of the NEXT
-    #      step's features runs on a copy stream while the current step computes (double buffering through a
-    #      staging buffer); every step still performs one H2D of its inputs and one D2H of its loss.
-    copy_stream = torch.cuda.Stream(device)
+    # launches per step: count one eager overlapped step (the capture contains exactly these launches)
+    lib.moma_debug_launch_count(1)
+    lib.moma_debug_flops(0, 1); lib.moma_debug_flops(1, 1)
+    cs.step_overlapped()
+    torch.cuda.synchronize()
+    out["gpu_launches_per_step"] = int(lib.moma_debug_launch_count(1))
+    out["gpu_launches"] = out["gpu_launches_per_step"] * steps
+    gemm_flop, attn_flop = float(lib.moma_debug_flops(0, 1)), float(lib.moma_debug_flops(1, 1))
+
+    # eager module API (what the unchanged helper/loops_moma.py drives), sequential order
+    for _ in range(3):
+        cs.step()
+    eager_ms = ctx.timed(cs.step, max(20, steps // 5)) / max(20, steps // 5)
+    out["eager"] = {"ms_per_step": eager_ms, "value": n / (eager_ms * 1e-3),
+                    "note": "same step through the eager module API in the reference loop's order (Python between kernels)"}
+
+    # ---- end to end: host (pinned) inputs -> device, replay, host read of the loss.  The H2D copy of the NEXT step's
+    #      features runs on a copy stream while the current step computes (double buffering through a staging buffer);
+    #      every step still performs one H2D of its inputs and one D2H of its loss.
+    copy_stream = torch.cuda.Stream(dev)
     stage_s, stage_t = torch.empty_like(cs.feat_s, requires_grad=False), torch.empty_like(cs.feat_t)
     ev_copied, ev_consumed = torch.cuda.Event(), torch.cuda.Event()
 
@@ -339,93 +377,278 @@ def run_ours(args, cfg, rank, world, local_rank):
 
     for _ in range(3):
         step_e2e()
-    e2e_ms = timed(step_e2e, args.steps)
-    sampler.stop_flag = True
-    sampler.join(timeout=1)
+    e2e_ms = ctx.timed(step_e2e, steps) / steps
+    out["e2e"] = {"value": n / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": cs.h2d_bytes,
+                  "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
+                  "path": "pinned host features -> H2D on a copy stream (double-buffered, overlapping the previous step) -> "
+                          "static device buffers, graph replay, loss.item()"}
 
-    # ---- per-kernel CUDA-event timing for the rooflines: cold L2 (flush first; the flush also hides
-    #      the launch gap, so e0 -> e1 brackets the kernel alone), median of 20 launches
-    def kernel_us(launch):
-        ts = []
-        for _ in range(20):
-            if flush is not None:
-                flush.fill_(1)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); launch(); e1.record()
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1) * 1e3)
-        ts.sort()
-        return ts[len(ts) // 2]
-
+    # ---- per-kernel: shares of the step (CUPTI) + isolated cold timings for the two north-star kernels
+    fam, other, err = kernel_shares(ctx, graphed)
     from moma_b200._lib import BF16
     plan = ops._EMA_PLANS[ops.plan_key([p.detach() for p in cs.student], [p.detach() for p in cs.teacher])]
-    ema_us = kernel_us(lambda: plan.run(ALPHA))
-    n_q = B * world
-    q_bf = torch.randn(n_q, D, device=device).to(torch.bfloat16)
-    shadow = cs.contrast._shadow_of(cs.contrast.memory_shard if world > 1 else cs.contrast.memory)
-    n_splits = ops.nce_num_splits(n_q, D, shadow.shape[0], BF16)
-    st_buf = torch.empty((3, n_splits, n_q), device=device)
-    o_buf = torch.empty((n_splits, n_q, D), device=device)
-    nce_us = kernel_us(lambda: _lib.check(lib.moma_nce_partial(
-        q_bf.data_ptr(), shadow.data_ptr(), n_q, D, shadow.shape[0], 1.0 / T_NCE, BF16, n_splits, st_buf[0].data_ptr(),
+    ema_us = ctx.kernel_us(lambda: plan.run(ALPHA))
+    q_bf = torch.randn(n, D, device=dev).to(torch.bfloat16)
+    shadow = cs.contrast._shadow_of(cs.contrast.memory_shard if cs.sharded else cs.contrast.memory)
+    n_splits = ops.nce_num_splits(n, D, shadow.shape[0], BF16)
+    st_buf = torch.empty((3, n_splits, n), device=dev)
+    o_buf = torch.empty((n_splits, n, D), device=dev)
+    nce_us = ctx.kernel_us(lambda: _lib.check(lib.moma_nce_partial(
+        q_bf.data_ptr(), shadow.data_ptr(), n, D, shadow.shape[0], 1.0 / T_NCE, BF16, n_splits, st_buf[0].data_ptr(),
         st_buf[1].data_ptr(), st_buf[2].data_ptr(), o_buf.data_ptr(), torch.cuda.current_stream().cuda_stream)))
+    out["rooflines"] = rooflines(ctx, name, cfg, cs, fam, nce_us, ema_us, gemm_flop, attn_flop, n_splits)
+    out["kernel_shares"] = {"families": fam, "unmatched": other, "error": err,
+                            "how": "CUPTI activity records (torch.profiler) of graph replays with the L2 flushed before each; "
+                                   "mean per replay; kernels on parallel branches overlap, so the sum exceeds the step time"}
+    return out, cs, graphed
 
-    ms_per_step = total_ms / args.steps
-    value = B * world / (ms_per_step * 1e-3)
-    e2e_value = B * world / (e2e_ms / args.steps * 1e-3)
 
-    # ---- rooflines (algorithmic work per launch)
-    k_local = K // world                              # n_q = B * world queries scored per rank (all-gathered)
-    nce_flop = 4.0 * n_q * k_local * D                # S = Q.Queue^T and P.Queue, 2 FLOP/MAC each
-    ema_bytes = 12.0 * cs.ema_elems                   # read ema, read src, write ema (fp32)
-    # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of one `ncu --set full` capture of the same
-    # kernels at this configuration, committed under profiles/ (null when no capture exists for this config / world size)
+def rooflines(ctx, name, cfg, cs, fam, nce_us, ema_us, gemm_flop, attn_flop, n_splits):
+    """Roofline entries for the kernels of the step (algorithmic work per step).  The first
+    entry of the returned list is the kernel family with the largest share of the step's kernel time."""
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
     traffic = {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(f"{args.config}_n{world}", {})
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(f"{name}_n{ctx.world}", {})
     except Exception:
         pass
     tf_peak = peaks.get("bf16_tflops_sustained", 1421.9)
+    tf_burst = peaks.get("bf16_tflops", 1676.7)
     bw_peak = peaks.get("hbm_gbs", 6452.2)
-    roof_nce = {"kernel": "nce_tc_kernel (tcgen05 InfoNCE logits+CE fwd/bwd)", "bound": "tensor",
-                "achieved": nce_flop / (nce_us * 1e-6) / 1e12 if nce_us else None, "peak": tf_peak, "unit": "TFLOP/s",
-                "frac": (nce_flop / (nce_us * 1e-6) / 1e12 / tf_peak) if nce_us else None, "traffic": traffic.get("nce_tc2_kernel"),
-                "us_per_launch": nce_us, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback"}
-    roof_ema = {"kernel": "ema_multi_kernel (momentum update)", "bound": "hbm",
-                "achieved": ema_bytes / (ema_us * 1e-6) / 1e9 if ema_us else None, "peak": bw_peak, "unit": "GB/s",
-                "frac": (ema_bytes / (ema_us * 1e-6) / 1e9 / bw_peak) if ema_us else None, "traffic": traffic.get("ema_multi_kernel"),
-                "algorithmic_bytes": ema_bytes,
-                "us_per_launch": ema_us, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback"}
-    dominant = roof_ema if ema_us >= nce_us else roof_nce
-    other = roof_nce if dominant is roof_ema else roof_ema
+    src = "MEASURED_PEAKS.json" if peaks else "fallback of B200_PROFILING.md"
+    world = ctx.world
+    n, D, K = cfg["B"] * world, cfg["D"], cfg["K"]
+    k_local = K // world
+    nce_flop = 4.0 * n * k_local * D                   # S = Q.Queue^T and P.Queue, 2 FLOP/MAC each
+    ema_bytes = 12.0 * cs.ema_elems                    # read ema, read src, write ema (fp32)
+    fam = fam or {}
 
+    def in_step(key):
+        d = fam.get(key)
+        return (d["us"], d["launches"]) if d else (None, None)
+
+    def tensor_entry(kernel, key, flop, us_alone=None, extra=None):
+        us_step, launches = in_step(key)
+        us = us_alone if us_alone is not None else us_step
+        e = {"kernel": kernel, "bound": "tensor", "unit": "TFLOP/s", "peak": tf_peak,
+             "peak_source": f"{src} bf16_tflops_sustained (burst {tf_burst})",
+             "algorithmic_flop_per_step": flop, "us_in_step": us_step, "launches_per_step": launches,
+             "us_per_launch": us_alone, "traffic": None}
+        if us:
+            e["achieved"] = flop / (us * 1e-6) / 1e12
+            e["frac"] = e["achieved"] / tf_peak
+        else:
+            e["achieved"] = e["frac"] = None
+        if us_step:
+            e["achieved_in_step"] = flop / (us_step * 1e-6) / 1e12
+            e["frac_in_step"] = e["achieved_in_step"] / tf_peak
+        e.update(extra or {})
+        return e
+
+    entries = [
+        tensor_entry("nce_tc2_kernel (tcgen05 InfoNCE logits + CE forward/backward)", "nce_tc", nce_flop, nce_us,
+                     {"traffic": traffic.get("nce_tc2_kernel"), "splits": n_splits,
+                      "timing": "achieved/frac: one launch alone, cold L2 (256 MiB flush read before it), CUDA events, "
+                                "median of 20; *_in_step: the same kernel inside the replayed step (CUPTI)"}),
+        tensor_entry("gemm3xtf32_kernel (projection heads + attention projections, 3xTF32 mma.sync)", "gemm3xtf32",
+                     gemm_flop, None, {"note": "algorithmic FLOP counted once (the kernel runs 3 tensor-core passes); "
+                                               "latency-bound launches of <= 0.3 GFLOP each"}),
+    ]
+    # attention core: forward and backward families together
+    a_f, a_b = fam.get("attn_fwd"), fam.get("attn_bwd")
+    if a_f or a_b:
+        us = (a_f["us"] if a_f else 0.0) + (a_b["us"] if a_b else 0.0)
+        ln = (a_f["launches"] if a_f else 0.0) + (a_b["launches"] if a_b else 0.0)
+        fam = dict(fam); fam["attn_core"] = {"us": us, "launches": ln}
+        entries.append(tensor_entry("attn_fwd_kernel + attn_bwd_dq/dkv_kernel (attention core, 3 modules fwd, atts_q bwd)",
+                                    "attn_core", attn_flop, None))
+    us_step, launches = (fam.get("ema") or {}).get("us"), (fam.get("ema") or {}).get("launches")
+    ema = {"kernel": "ema_multi_kernel (momentum update, ResNet-18 pair)", "bound": "hbm", "unit": "GB/s", "peak": bw_peak,
+           "peak_source": f"{src} hbm_gbs", "algorithmic_bytes": ema_bytes, "us_per_launch": ema_us, "us_in_step": us_step,
+           "launches_per_step": launches, "achieved": ema_bytes / (ema_us * 1e-6) / 1e9,
+           "frac": ema_bytes / (ema_us * 1e-6) / 1e9 / bw_peak, "traffic": traffic.get("ema_multi_kernel"),
+           "note": "the results (1/3 of the algorithmic bytes) are still dirty in the 126 MB L2 when the kernel ends: the "
+                   "DRAM-side rate is traffic / us_per_launch (dram_frac)"}
+    if ema["traffic"]:
+        ema["dram_frac"] = ema["traffic"] / (ema_us * 1e-6) / 1e9 / bw_peak
+    entries.append(ema)
+    entries.sort(key=lambda e: e.get("us_in_step") or 0.0, reverse=True)
+    total = sum(d["us"] for k_, d in fam.items() if k_ != "attn_core") or 1.0
+    for e in entries:
+        e["share_of_kernel_time"] = (e.get("us_in_step") or 0.0) / total
+    return entries
+
+
+# ----------------------------------------------------------------------------- C4: small-student EMA
+def c4_ema_lines(ctx: Ctx):
+    """EMA (momentum_update) of the small students of BASELINE config C4 against their same-architecture momentum
+    twins: EfficientNet-B0 (213 tensors) and MobileNetV2 (158 tensors); tensor lists from the reference's model
+    definitions (bench_data/c4_param_shapes.json, scripts/make_c4_shapes.py).  HBM-bound: 12 B / element."""
+    from moma_b200 import ops
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    bw_peak = peaks.get("hbm_gbs", 6452.2)
+    shapes = json.load(open(os.path.join(ROOT, "bench_data", "c4_param_shapes.json")))
+    out = {}
+    for name in ("efficientnet_b0", "mobilenetv2_imagenet", "resnet50"):
+        torch.manual_seed(1)
+        src = [torch.randn(*s, device=ctx.device) for s in shapes[name]["shapes"]]
+        dst = [torch.randn(*s, device=ctx.device) for s in shapes[name]["shapes"]]
+        ops.ema_update(src, dst, ALPHA)
+        plan = ops._EMA_PLANS[ops.plan_key(src, dst)]
+        us = ctx.kernel_us(lambda: plan.run(ALPHA))
+        nbytes = 12.0 * shapes[name]["elements"]
+        out[name] = {"tensors": shapes[name]["tensors"], "elements": shapes[name]["elements"], "launches": 1,
+                     "us_per_launch": us, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (us * 1e-6) / 1e9,
+                     "frac_of_hbm_peak": nbytes / (us * 1e-6) / 1e9 / bw_peak,
+                     "floor_us_at_peak": nbytes / bw_peak / 1e3}
+        del src, dst
+    # enqueue (+ bf16 shadow) at C2's n = 256, D = 128: 328 KB -- latency, reported honestly in us and GB/s
+    K, D, n = 16384, 128, 256
+    q32 = torch.zeros(K, D, device=ctx.device); q16 = torch.zeros(K, D, device=ctx.device, dtype=torch.bfloat16)
+    keys = torch.randn(n, D, device=ctx.device)
+    us = ctx.kernel_us(lambda: ops.enqueue(keys, q32, q16, K, 100))
+    nb = n * D * (4 + 4 + 2)
+    out["enqueue_n256_d128"] = {"us_per_launch": us, "algorithmic_bytes": nb, "achieved_gbs": nb / (us * 1e-6) / 1e9,
+                                "note": "too small to be bandwidth-bound (floor 0.05 us); launch latency"}
+    out["peak_gbs"] = bw_peak
+    torch.cuda.empty_cache()
+    return out
+
+
+# ----------------------------------------------------------------------------- the reference's own GPU behaviour
+def gpu_reference(ctx: Ctx, cfg, steps):
+    """the reference's op sequence (oracle/torch_port.py, pinned to the reference) executed by
+    the stock PyTorch / ATen / cuBLAS kernels on this GPU -- eager fp32 (its true behaviour), eager with bf16 GEMM
+    operands for the negatives (the library tensor-core bar), and each captured in a CUDA graph (no Python between
+    kernels).  A baseline measured beside the repo's step; none of it is on the product path."""
+    from oracle.torch_port import PortCriterionStep
+    out = {}
+    B = cfg["B"]
+    steps = max(10, min(steps, 50))
+    for tag, od in (("fp32", None), ("bf16_operands", torch.bfloat16)):
+        port = PortCriterionStep(cfg["s_dim"], cfg["t_dim"], cfg["D"], cfg["K"], T_NCE, ALPHA, cfg["H"],
+                                 resnet18_param_shapes(), seed=SEED, device=ctx.device, operand_dtype=od)
+        torch.manual_seed(SEED + 1)
+        fs = torch.randn(B, cfg["s_dim"], device=ctx.device, requires_grad=True)
+        ft = torch.randn(B, cfg["t_dim"], device=ctx.device)
+        for _ in range(3):
+            port.step(fs, ft)
+        ms = ctx.timed(lambda: port.step(fs, ft), steps) / steps
+        out[f"eager_{tag}_ms"] = ms
+        try:
+            port.contrast.device_constants = True
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=torch.cuda.current_stream()):
+                port.step(fs, ft)
+            for _ in range(3):
+                g.replay()
+            out[f"graphed_{tag}_ms"] = ctx.timed(g.replay, steps) / steps
+            del g
+        except Exception as e:                           # the port is eager code: report why it did not capture
+            out[f"graphed_{tag}_ms"] = None
+            out[f"graphed_{tag}_error"] = f"{type(e).__name__}: {str(e)[:160]}"
+        del port
+        torch.cuda.empty_cache()
+    out["note"] = ("reference op sequence on stock PyTorch GPU kernels (cuBLAS SGEMM / bf16 GEMM, ATen softmax/CE), same "
+                   "workload, L2 flushed before each step; graphed_* bakes the ring pointer into the capture (timing only)")
+    return out
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args, rank, world, local_rank):
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    # everything runs on one side stream from the first call on (graph capture needs a non-default stream, and autograd
+    # binds gradient accumulation to the stream a leaf was first used on).  High priority: the student chain (this
+    # stream) is the critical path of the step.
+    torch.cuda.set_stream(torch.cuda.Stream(device, priority=-1))
+    ctx = Ctx(args, rank, world, local_rank)
+    steps = args.steps
+    name = args.config
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    main, cs, graphed = measure(ctx, name, CONFIGS[name], steps, strong=False, full=True)
+    sampler.stop_flag = True
+    sampler.join(timeout=1)
+    if "error" in main:
+        return main, 3
+
+    roofs = main.pop("rooflines")
+    north = next((r for r in roofs if r["kernel"].startswith("nce_tc2")), None)
+    cfg = CONFIGS[name]
     out = {
-        "metric": "MoMA criterion samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "metric": "MoMA criterion samples/sec", "value": main["value"], "unit": "samples/s", "n_gpus": world,
+        "steps": steps, "warmup": max(args.warmup, 3) + 5, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": cfg["desc"], "global_batch": B * world, "feat_dim": D, "queue_K": K,
-                   "s_dim": cfg["s_dim"], "t_dim": cfg["t_dim"], "heads": cfg["H"], "nce_t": T_NCE, "alpha": ALPHA,
-                   "head": "mlp", "attn": "self", "ema_pair": "ResNet-18 student -> ResNet-18 momentum twin (11.18M)",
-                   "queue": "replicated" if world == 1 else f"sharded by K over {world} ranks (cyclic)",
+        "config": {"workload": cfg["desc"], "global_batch": main["global_batch"], "per_gpu_batch": cfg["B"],
+                   "feat_dim": cfg["D"], "queue_K": cfg["K"], "s_dim": cfg["s_dim"], "t_dim": cfg["t_dim"],
+                   "heads": cfg["H"], "nce_t": T_NCE, "alpha": ALPHA, "head": "mlp", "attn": "self",
+                   "ema_pair": "ResNet-18 student -> ResNet-18 momentum twin (11.18M)", "queue": main["queue"],
                    "l2": "no flush" if args.no_flush else "L2 flushed (256 MiB read) before every step; per-step CUDA events summed",
+                   "precision_note": "bf16 InfoNCE operands, fp32 accumulation; parity bar 1e-3 vs the oracle fed the same "
+                                     "bf16-rounded operands (against the un-rounded fp32 reference the gradient differs by "
+                                     "1.4-1.6e-3: operand rounding, DESIGN.md section 7)",
                    "timed_region": "EMA + projection heads + 3x attention + fused InfoNCE/CE fwd+bwd + enqueue (criterion step, L1)"},
-        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": cs.h2d_bytes, "d2h_bytes_per_step": 4,
-                "ms_per_step": e2e_ms / args.steps,
-                "path": "pinned host features -> H2D on a copy stream (double-buffered, overlapping the previous step) -> "
-                        "static device buffers, graph replay, loss.item()"},
-        "gpu_launches": launches,
-        "gpu_launches_per_step": launches_per_step,
-        "eager": {"ms_per_step": eager_ms / args.steps, "value": B * world / (eager_ms / args.steps * 1e-3),
-                  "note": "same step through the eager module API (Python between kernels)"},
+        "parity_check": main["parity_check"],
+        "e2e": main["e2e"], "gpu_launches": main["gpu_launches"], "gpu_launches_per_step": main["gpu_launches_per_step"],
+        "eager": main["eager"],
         "execution": "whole criterion step (fwd+bwd) captured once as a CUDA graph and replayed; the teacher branch, the "
                      "queue-attention + enqueue branch and the backbone EMA are forked onto side streams inside the capture; "
                      "kernels are chained with programmatic dependent launch",
-        "roofline": dominant, "roofline_other": other,
+        "roofline": roofs[0], "roofline_north_star": north, "roofline_all": roofs,
+        "kernel_shares": main["kernel_shares"],
         "clocks": sampler.summary(),
     }
+    if world > 1:
+        out["exchange"] = main.get("exchange")
+    del cs, graphed
+    torch.cuda.empty_cache()
+
+    rc = 0
+    if not args.quick:
+        extra = {}
+        plan = [("C2", False), ("C5", False)] if world == 1 else [("C3", True), ("C5", True), ("C2", False)]
+        for cname, strong in plan:
+            if cname == name and not strong:
+                continue
+            if strong and CONFIGS[cname]["B"] % world:
+                continue
+            key = f"{cname}_{'strong' if strong else 'weak'}" if world > 1 else cname
+            try:
+                blk, c2, g2 = measure(ctx, cname, CONFIGS[cname], max(20, steps // 2), strong=strong, full=(world == 1 and cname == "C2"))
+                del c2, g2
+            except Exception as e:
+                blk = {"config": cname, "error": f"{type(e).__name__}: {str(e)[:300]}"}
+            torch.cuda.empty_cache()
+            if "rooflines" in blk:
+                blk["roofline_all"] = blk.pop("rooflines")
+            extra[key] = blk
+            if "error" in blk:
+                rc = 3
+        out["other_configs"] = extra
+        if rank == 0:
+            try:
+                out["c4_small_student_ema"] = c4_ema_lines(ctx)
+            except Exception as e:
+                out["c4_small_student_ema"] = {"error": f"{type(e).__name__}: {e}"}
+        if world == 1:
+            try:
+                out["gpu_reference"] = gpu_reference(ctx, CONFIGS[name], steps)
+                out["gpu_reference"]["ours_ms"] = main["ms_per_step"]
+                out["gpu_reference"]["ours_eager_ms"] = main["eager"]["ms_per_step"]
+            except Exception as e:
+                out["gpu_reference"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(cfg, budget_s=args.cpu_seconds)
-    return out
+        out["cpu_baseline"] = cpu_baseline(CONFIGS[name], budget_s=args.cpu_seconds)
+    return out, rc
 
 
 # ----------------------------------------------------------------------------- CPU arm
@@ -469,9 +692,14 @@ def run_reference(args, cfg, rank, world):
     torch.manual_seed(SEED + 1)
     fs = torch.randn(B, cfg["s_dim"], requires_grad=True)
     ft = torch.randn(B, cfg["t_dim"])
-    steps = min(steps, 200)
-    for _ in range(min(max(args.warmup, 1), 5)):
+    warm = min(max(args.warmup, 1), 3)
+    for _ in range(warm):
         port.step(fs, ft)
+    # bounded sample: at most ~90 s of CPU work whatever --steps says
+    t0 = time.perf_counter()
+    port.step(fs, ft)
+    one = time.perf_counter() - t0
+    steps = max(1, min(steps, 200, int(90.0 / max(one, 1e-3))))
     t0 = time.perf_counter()
     for _ in range(steps):
         port.step(fs, ft)
@@ -479,12 +707,15 @@ def run_reference(args, cfg, rank, world):
     value = B * steps / dt
     return {
         "impl": "reference", "metric": "MoMA criterion samples/sec", "value": value, "unit": "samples/s",
-        "n_gpus": world, "steps": steps, "warmup": min(max(args.warmup, 1), 5), "ms_per_step": dt / steps * 1e3,
+        "n_gpus": world, "steps": steps, "warmup": warm + 1, "ms_per_step": dt / steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["desc"], "global_batch": B, "feat_dim": cfg["D"], "queue_K": cfg["K"],
-                   "note": "reference CPU path (pinned torch port of the reference op sequence), one replica on rank 0"},
+        "config": {"workload": cfg["desc"], "global_batch": B * world, "per_gpu_batch": B, "feat_dim": cfg["D"],
+                   "queue_K": cfg["K"], "s_dim": cfg["s_dim"], "t_dim": cfg["t_dim"], "heads": cfg["H"], "nce_t": T_NCE,
+                   "alpha": ALPHA, "head": "mlp", "attn": "self",
+                   "note": "reference CPU path (pinned torch port of the reference op sequence): ONE replica of the per-GPU "
+                           "batch on rank 0, whatever N is -- at N > 1 compare per-GPU throughput, not the aggregate"},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{steps} full criterion steps, fp32, all host threads"},
+                         "sample": f"{steps} full criterion steps (B={B}), fp32, all host threads"},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -496,10 +727,11 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
+    ap.add_argument("--config", default="C3", choices=sorted(CONFIGS))
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--quick", action="store_true", help="headline configuration only (no extra blocks)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
 
@@ -511,7 +743,7 @@ def main():
         out = run_reference(args, cfg, rank, world)
         if out is not None:
             print(json.dumps(out), flush=True)
-        return
+        return 0
 
     import torch.distributed as dist
     # stdout carries exactly one JSON line: everything else any library prints on fd 1 (e.g. NCCL's version
@@ -522,14 +754,15 @@ def main():
     if world > 1:
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    out = run_ours(args, cfg, rank, world, local_rank)
+    out, rc = run_ours(args, rank, world, local_rank)
     if rank == 0:
         json_out.write(json.dumps(out) + "\n")
         json_out.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    return rc
 
 
 if __name__ == "__main__":
-    main()
+    sys.exit(main())

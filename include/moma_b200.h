@@ -262,6 +262,10 @@ int moma_debug_nce_tc(const void *q, const void *queue, int64_t B, int64_t D, in
 int moma_debug_tc_error(void);
 /* number of kernels this library has launched in this process (optionally reset to 0) */
 long long moma_debug_launch_count(int reset);
+/* ALGORITHMIC floating-point operations issued since the last reset (for bench.py's rooflines):
+ * kind 0 = Linear GEMMs of moma_linear_* / the attention projections (2*M*N*K each, counted once although the
+ * 3xTF32 kernel runs three tensor-core passes), kind 1 = attention core (forward 4*Nq*N*C, backward 8*N*N*C). */
+double moma_debug_flops(int kind, int reset);
 
 #ifdef __cplusplus
 }

@@ -162,6 +162,8 @@ class ContrastTrainer(BaseTrainer):
         else:
             dist.broadcast(contrast.memory_s, 0)
             dist.broadcast(contrast.memory_t, 0)
+        if hasattr(contrast, "invalidate_shadows"):      # the collective wrote the masters behind autograd's back
+            contrast.invalidate_shadows()
 
     @staticmethod
     def _global_gather(x):

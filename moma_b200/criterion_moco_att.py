@@ -147,7 +147,7 @@ class Attention(nn.Module):
         with torch.no_grad():
             if not self._fusable(x_local):
                 return self._composed(gather(x_local))[q_start::q_stride][:q_count]
-            qkv_local = ops.linear(x_local, self.qkv.weight, self.qkv.bias, key=("rows_gathered", id(self)))
+            qkv_local = ops.linear(x_local, self.qkv.weight, self.qkv.bias, key="rows_gathered")
             return ops.attention_rows_from_qkv(gather(qkv_local), self.proj.weight, self.proj.bias, self.num_heads,
                                                q_start, q_stride, q_count)
 
@@ -221,7 +221,7 @@ class _Head(nn.Sequential):
                         torch.backends.cuda.matmul.allow_tf32 = prev
                 else:
                     relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
-                    x = ops.linear(x, m.weight, m.bias, relu=relu, key=id(m))
+                    x = ops.linear(x, m.weight, m.bias, relu=relu)
                     i += 1 if relu else 0
             else:
                 x = m(x)

@@ -8,6 +8,7 @@
 //   matching reshape(B, N, 3, H, hd) at :157) -> per head softmax(q k^T * hd^-0.5) v
 //   -> o [N, C] (heads merged, :164) -> y = o W_proj^T + b_proj (:165).
 #include <math_constants.h>
+#include <mutex>
 #include "common.cuh"
 
 namespace moma {
@@ -524,8 +525,7 @@ template <int HD, int RW> static size_t dkv_smem() {
 template <int HD, int RW>
 static void launch_fwd_rw(const float* qkv, int N, int C, int H, float scale, float* o, float* lse, cudaStream_t st,
                           int q_start, int q_stride, int NQ) {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(attn_fwd_kernel<HD, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem<HD, RW>()); attr = true; }
+    ensure_dyn_smem(reinterpret_cast<const void*>(attn_fwd_kernel<HD, RW>), (int)fwd_smem<HD, RW>());
     constexpr int AR = 4 * RW;
     launch_pdl(attn_fwd_kernel<HD, RW>, dim3((NQ + AR - 1) / AR, H), dim3(kAThreads), fwd_smem<HD, RW>(), st, qkv, N, C, scale, o, lse,
                q_start, q_stride, NQ);
@@ -533,12 +533,8 @@ static void launch_fwd_rw(const float* qkv, int N, int C, int H, float scale, fl
 template <int HD, int RW>
 static void launch_bwd_rw(const float* qkv, const float* dO, const float* lse, const float* delta, int N, int C, int H,
                           float scale, float* dqkv, cudaStream_t st, cudaStream_t st2, bool dkv_split) {
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(attn_bwd_dq_kernel<HD, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dq_smem<HD, RW>());
-        cudaFuncSetAttribute(attn_bwd_dkv_kernel<HD, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dkv_smem<HD, RW>());
-        attr = true;
-    }
+    ensure_dyn_smem(reinterpret_cast<const void*>(attn_bwd_dq_kernel<HD, RW>), (int)dq_smem<HD, RW>());
+    ensure_dyn_smem(reinterpret_cast<const void*>(attn_bwd_dkv_kernel<HD, RW>), (int)dkv_smem<HD, RW>());
     constexpr int AR = 4 * RW;
     const dim3 grid((N + AR - 1) / AR, H);
     // dQ and dK/dV are independent: two streams (st2 was forked from st by the caller)
@@ -562,6 +558,7 @@ template <int HD>
 static void launch_fwd(const float* qkv, int N, int C, int H, float scale, float* o, float* lse, cudaStream_t st,
                        int q_start = 0, int q_stride = 1, int NQ = -1) {
     if (NQ < 0) NQ = N;
+    note_flops(1, 4.0 * NQ * N * C);                      // Q K^T and P V, 2 FLOP per MAC
     switch (pick_rw<HD>(NQ, H)) {
         case 8: launch_fwd_rw<HD, 8>(qkv, N, C, H, scale, o, lse, st, q_start, q_stride, NQ); break;
         case 4: launch_fwd_rw<HD, 4>(qkv, N, C, H, scale, o, lse, st, q_start, q_stride, NQ); break;
@@ -580,6 +577,7 @@ static bool dkv_wants_split(int N, int H) {
 template <int HD>
 static void launch_bwd(const float* qkv, const float* dO, const float* lse, const float* delta, int N, int C, int H,
                        float scale, float* dqkv, cudaStream_t st, cudaStream_t st2, bool dkv_split) {
+    note_flops(1, 8.0 * N * N * C);                       // dV, dP, dQ, dK (the recomputed scores are not counted)
     switch (pick_rw<HD>(N, H)) {
         case 8: launch_bwd_rw<HD, 8>(qkv, dO, lse, delta, N, C, H, scale, dqkv, st, st2, dkv_split); break;
         case 4: launch_bwd_rw<HD, 4>(qkv, dO, lse, delta, N, C, H, scale, dqkv, st, st2, dkv_split); break;
@@ -595,17 +593,22 @@ struct BwdStreams {
     bool ok = false;
 };
 static BwdStreams& bwd_streams() {
-    static BwdStreams b;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    // one set per device, created once under std::call_once (streams and events belong to a device)
+    constexpr int kMaxDev = 64;
+    static BwdStreams per_dev[kMaxDev];
+    static std::once_flag once[kMaxDev];
+    static BwdStreams none;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) { cudaGetLastError(); return none; }
+    BwdStreams& b = per_dev[dev];
+    std::call_once(once[dev], [&b] {
         bool good = cudaStreamCreateWithFlags(&b.s1, cudaStreamNonBlocking) == cudaSuccess &&
                     cudaStreamCreateWithFlags(&b.s2, cudaStreamNonBlocking) == cudaSuccess;
         cudaEvent_t* evs[] = {&b.fork, &b.d_o, &b.dq, &b.dkv, &b.join1, &b.join2};
         for (auto e : evs) good = good && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
         b.ok = good;
         if (!good) cudaGetLastError();
-    }
+    });
     return b;
 }
 

@@ -19,18 +19,28 @@ int fail(int code, const char* fmt, ...);
         if (!(cond)) return ::moma::fail((code), __VA_ARGS__); \
     } while (0)
 
+// Launch errors: launch_pdl() records the first failing cudaLaunchKernelEx of the calling thread (take_launch_error()),
+// so helpers that launch several kernels and return void still surface it at the entry point's check.
+void note_launch_error(cudaError_t e);
+cudaError_t take_launch_error();            // returns and clears the calling thread's first recorded launch error
 #define MOMA_CUDA_LAUNCH_CHECK(what)                                                   \
     do {                                                                               \
-        cudaError_t _e = cudaGetLastError();                                           \
+        cudaError_t _e = ::moma::take_launch_error();                                  \
+        const cudaError_t _l = cudaGetLastError();                                     \
+        if (_e == cudaSuccess) _e = _l;                                                \
         if (_e != cudaSuccess)                                                         \
             return ::moma::fail(MOMA_ERR_CUDA, "%s: %s", (what), cudaGetErrorString(_e)); \
     } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device), thread-safe.
+cudaError_t ensure_dyn_smem(const void* func, int bytes);
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline cudaStream_t as_stream(moma_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
-int sm_count();
-void note_launches(int n);   // launch counter behind moma_debug_launch_count()   // cached multiprocessor count of the current device (148 on B200)
+int sm_count();     // cached multiprocessor count of the current device (148 on B200)
+void note_launches(int n);   // launch counter behind moma_debug_launch_count()
+void note_flops(int kind, double flops);   // algorithmic-FLOP counters behind moma_debug_flops(): 0 = Linear GEMMs, 1 = attention core
 
 // gemm.cu: C[M,N] = act(A B^T + bias) on the tensor cores (3xTF32); see the file header for the operand convention
 int gemm_splits(int M, int N, int K);
@@ -54,7 +64,9 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, KArgs(static_cast<Args&&>(args))...);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(static_cast<Args&&>(args))...);
+    if (e != cudaSuccess) note_launch_error(e);
+    return e;
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -345,6 +345,7 @@ size_t gemm_workspace_bytes(int M, int N, int K) {
 int gemm_nt(const float* A, const float* a_mask, int64_t a_rs, int64_t a_cs, const float* Bm, int64_t b_rs, int64_t b_cs,
             const float* bias, float* C, int64_t ldc, int M, int N, int K, int relu, void* workspace, size_t workspace_bytes,
             cudaStream_t st, void* c_bf16) {
+    note_flops(0, 2.0 * M * N * K);
     GemmParams p;
     p.a = Operand{A, a_rs, a_cs, M, operand_mode(A, a_mask, a_rs, a_cs, M, K)};
     p.b = Operand{Bm, b_rs, b_cs, N, operand_mode(Bm, nullptr, b_rs, b_cs, N, K)};

@@ -406,14 +406,12 @@ static int partial_f32(const float* q, const float* queue, int64_t B, int64_t D,
     if (D <= 256) {
         constexpr int BN = 64;
         const size_t smem = (size_t)(kBM * ld + BN * ld + kBM * (BN + 4)) * sizeof(float);
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(nce_partial_f32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = true; }
+        ensure_dyn_smem(reinterpret_cast<const void*>(nce_partial_f32_kernel<BN>), 160 * 1024);
         nce_partial_f32_kernel<BN><<<grid, kSimtThreads, smem, st>>>(q, queue, (int)B, (int)D, K, inv_T, n_splits, pm, pl, pmm, pO);
     } else {
         constexpr int BN = 32;
         const size_t smem = (size_t)(kBM * ld + BN * ld + kBM * (BN + 4)) * sizeof(float);
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(nce_partial_f32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = true; }
+        ensure_dyn_smem(reinterpret_cast<const void*>(nce_partial_f32_kernel<BN>), 160 * 1024);
         nce_partial_f32_kernel<BN><<<grid, kSimtThreads, smem, st>>>(q, queue, (int)B, (int)D, K, inv_T, n_splits, pm, pl, pmm, pO);
     }
     MOMA_CUDA_LAUNCH_CHECK("nce_partial(f32)");

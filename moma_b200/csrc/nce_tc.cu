@@ -901,11 +901,10 @@ static int launch2(const void* q, const void* queue, int64_t B, int64_t K_local,
     if (rc != MOMA_OK) return rc;
     rc = cached_map(&mk, queue, K_local, D, C::BN);
     if (rc != MOMA_OK) return rc;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(nce_tc2_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_TOTAL);
+    {
+        const cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(nce_tc2_kernel<D>), C::SMEM_TOTAL);
+        if (e != cudaSuccess) take_launch_error();
         MOMA_REQUIRE(e == cudaSuccess, MOMA_ERR_CUDA, "nce_tc2: smem attribute: %s", cudaGetErrorString(e));
-        attr = true;
     }
     const dim3 grid((unsigned)((B + kBM - 1) / kBM), (unsigned)n_splits);
     const float scale_log2 = inv_T * 1.4426950408889634f;
@@ -927,11 +926,10 @@ static int launch(const void* q, const void* queue, int64_t B, int64_t K_local, 
     if (rc != MOMA_OK) return rc;
     rc = cached_map(&mk, queue, K_local, D, BN);
     if (rc != MOMA_OK) return rc;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(nce_tc_kernel<D, NQ, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_TOTAL);
+    {
+        const cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(nce_tc_kernel<D, NQ, BN>), C::SMEM_TOTAL);
+        if (e != cudaSuccess) take_launch_error();
         MOMA_REQUIRE(e == cudaSuccess, MOMA_ERR_CUDA, "nce_tc: smem attribute: %s", cudaGetErrorString(e));
-        attr = true;
     }
     const dim3 grid((unsigned)((B + NQ * kBM - 1) / (NQ * kBM)), (unsigned)n_splits);
     const float scale_log2 = inv_T * 1.4426950408889634f;

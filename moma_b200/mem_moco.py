@@ -31,8 +31,10 @@ class BaseMoCo(nn.Module):
         self.K = K
         self.T = T
         self.index = 0
-        self._shadows = {}          # buffer name -> (bf16 shadow, data_ptr, version) ; non-persistent
+        self._shadows = {}          # registered buffer name -> (bf16 shadow, version) ; non-persistent
         self._zero_labels = {}
+        self._pending = []          # (queue data_ptr, LazyLogits state | ops.QueueGuard) awaiting the next enqueue
+        self.checkpoint_pointer = False   # True: state_dict() also carries the ring pointer (key '<prefix>index')
 
     # ---- pointer / enqueue ------------------------------------------------
     def _update_pointer(self, bsz):
@@ -57,14 +59,33 @@ class BaseMoCo(nn.Module):
         """Account on the host for one graph replay that enqueued ``n_rows`` rows."""
         self.index = (self.index + n_rows) % self.K
 
+    def _buffer_name(self, queue: torch.Tensor):
+        """Name of the registered buffer `queue` is (or is a detached alias of), else None."""
+        for name, b in self._buffers.items():
+            if b is not None and (b is queue or (b.data_ptr() == queue.data_ptr() and b.shape == queue.shape)):
+                return name
+        return None
+
     def _shadow_of(self, queue: torch.Tensor, create: bool = True):
-        """bf16 shadow of a queue buffer, rebuilt when the fp32 master was replaced or
-        modified behind our back (``.cuda()``, ``load_state_dict``, ``broadcast_memory``)."""
+        """bf16 shadow of a queue.  Shadows are cached only for REGISTERED buffers (by buffer name) and rebuilt
+        when the fp32 master was replaced (``.cuda()``, ``load_state_dict``) or modified through autograd-visible
+        in-place ops (``_version``); writers that bypass the version counter (``memory.data.copy_``,
+        ``dist.broadcast``) must call ``invalidate_shadows()``.  A transient queue (e.g. the attended queue of
+        MoCoAtt, a new tensor every step whose address the allocator recycles) is cast every time."""
         if not queue.is_cuda or queue.shape[1] % 8 != 0:
             return None
-        for name, (sh, ptr, ver) in list(self._shadows.items()):
-            if ptr == queue.data_ptr():
-                if ver != queue._version or sh.device != queue.device:
+        name = self._buffer_name(queue)
+        if name is None:
+            if not create:
+                return None
+            sh = torch.empty(queue.shape, dtype=torch.bfloat16, device=queue.device)
+            ops.cast_bf16(queue.contiguous(), sh)
+            return sh
+        ent = self._shadows.get(name)
+        if ent is not None:
+            sh, ptr, ver = ent
+            if ptr == queue.data_ptr() and sh.device == queue.device and sh.shape == queue.shape:
+                if ver != queue._version:
                     ops.cast_bf16(queue, sh)
                     self._shadows[name] = (sh, ptr, queue._version)
                 return sh
@@ -72,24 +93,80 @@ class BaseMoCo(nn.Module):
             return None
         sh = torch.empty(queue.shape, dtype=torch.bfloat16, device=queue.device)
         ops.cast_bf16(queue, sh)
-        if len(self._shadows) > 4:
-            self._shadows.clear()
-        self._shadows[f"s{len(self._shadows)}"] = (sh, queue.data_ptr(), queue._version)
+        self._shadows[name] = (sh, queue.data_ptr(), queue._version)
         return sh
+
+    def invalidate_shadows(self):
+        """Drop the bf16 shadows (call after writing a queue buffer behind autograd's back)."""
+        self._shadows.clear()
 
     def _update_memory(self, k, queue):
         """queue[(index + j) % K] = k[j]   (mem_moco.py:17-27)"""
         with torch.no_grad():
-            if k.shape[0] > self.K:
-                raise RuntimeError(f"enqueue of {k.shape[0]} rows into a queue of K={self.K}: duplicate ids "
+            n = k.shape[0]
+            if n > self.K:
+                raise RuntimeError(f"enqueue of {n} rows into a queue of K={self.K}: duplicate ids "
                                    "(undefined in the reference, mem_moco.py:24-27)")
             shadow = self._shadow_of(queue, create=ops.get_precision() == "bf16")
+            self._settle_pending(queue, shadow, n)
             ops.enqueue(k, queue, shadow, self.K, self.index, index_dev=self._index_dev)
+
+    def _settle_pending(self, queue, shadow, n):
+        """Before `queue` is overwritten: hand the n rows about to be replaced to everything that was computed
+        from the pre-enqueue queue and may still need it -- lazy logits handles that allow late materialisation
+        and the autograd nodes of dense logits (the reference's ``memory.clone()``, mem_moco.py:89, without
+        copying K x D every step)."""
+        ptr = queue.data_ptr()
+        mine = [o for (p, o) in self._pending if p == ptr]
+        self._pending = [(p, o) for (p, o) in self._pending if p != ptr]
+        if not mine or n == 0:
+            return
+        ids = ops.enqueue_ids(n, self.index, self.K, queue.device, index_dev=self._index_dev)
+        old32 = old16 = None
+        for o in mine:
+            if isinstance(o, ops.QueueGuard):
+                if old32 is None:
+                    old32 = queue.index_select(0, ids)
+                o.remember(ids, old32)
+            else:                                   # LazyLogits enqueue state
+                if shadow is not None and ops.get_precision() == "bf16":
+                    if old16 is None:
+                        old16 = shadow.index_select(0, ids)
+                    o["saved"] = (ids, old16)
+                else:
+                    if old32 is None:
+                        old32 = queue.index_select(0, ids)
+                    o["saved"] = (ids, old32)
+
+    # ---- checkpointing of the ring pointer (SURVEY 8f-4; the reference never saves it, train_student_moma.py:549-573)
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        super()._save_to_state_dict(destination, prefix, keep_vars)
+        if self.checkpoint_pointer:                  # opt-in: the default key set stays the reference's
+            destination[prefix + "index"] = torch.tensor(int(self.index), dtype=torch.int64)
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                              error_msgs):
+        key = prefix + "index"
+        if key in state_dict:
+            self.index = int(state_dict.pop(key)) % self.K
+            if self._index_dev is not None:
+                self._index_dev.fill_(self.index)
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                                      error_msgs)
+        self._shadows.clear()                        # the masters were just rewritten
 
     # ---- logits -----------------------------------------------------------
     def _compute_logit(self, q, k, queue):
-        """Dense logits (mem_moco.py:29-49); used by the variants' fallbacks and tests."""
-        out = ops.nce_logits(q, k, queue, self.T)
+        """Dense logits (mem_moco.py:29-49); used by the variants' fallbacks and tests.  When `queue` is one of
+        this module's live buffers, the rows a later enqueue overwrites are handed to the autograd node first
+        (``_settle_pending``), so ``backward()`` after the queue update still differentiates the logits that
+        were returned (the reference clones the queue for this, :89)."""
+        guard = None
+        if torch.is_grad_enabled() and q.requires_grad:
+            guard = ops.QueueGuard()                # a transient queue (never enqueued into) needs no copy either
+            if self._buffer_name(queue) is not None:
+                self._pending.append((queue.data_ptr(), guard))
+        out = ops.nce_logits(q, k, queue, self.T, guard)
         return out.squeeze().contiguous()
 
     def _compute_logit_qk(self, q, k):
@@ -131,18 +208,19 @@ class BaseMoCo(nn.Module):
         shape = (bsz, K + 1) if bsz != 1 else (K + 1,)
         handle = LazyLogits(shape, q.device, nce, labels, materialize)
         handle._enqueue_state = state
+        if self._buffer_name(queue) is not None:
+            if getattr(self, "track_overwritten", False):
+                self._pending.append((queue.data_ptr(), state))
+            else:
+                state["stale"] = True               # armed by _arm_stale() once the queue is updated
         return handle
 
-    def _remember_overwritten(self, handles, queue, n):
-        """Save the n queue rows the coming enqueue overwrites (n x D, tiny) for late materialisation."""
-        live = [h for h in handles if isinstance(h, LazyLogits)]
-        if not live or n == 0:
-            return
-        ids = ops.enqueue_ids(n, self.index, self.K, queue.device)
-        src = self._shadow_of(queue, create=False)
-        old = (src if (src is not None and ops.get_precision() == "bf16") else queue).index_select(0, ids)
-        for h in live:
-            h._enqueue_state["saved"] = (ids, old)
+    @staticmethod
+    def _arm_stale(handles):
+        """After the enqueue the dense logits of a handle that did not keep the overwritten rows are gone."""
+        for h in handles:
+            if isinstance(h, LazyLogits) and h._enqueue_state.get("stale") and h._dense is None:
+                h._materialize = _stale_after_enqueue
 
 
 class MoCo(BaseMoCo):
@@ -153,7 +231,8 @@ class MoCo(BaseMoCo):
         # same RNG draw as the reference: K*n_dim normals from the global CPU generator, then L2 rows
         self.register_buffer(mem_name, torch.randn(K, n_dim))
         self.memory = F.normalize(self.memory)
-        self.track_overwritten = False      # set True to allow materialising logits after the enqueue
+        self.track_overwritten = False      # True: keep the n overwritten rows so the dense logits can still be
+                                            # materialised after the enqueue (2 tiny extra launches per step)
 
     def forward(self, q, k, all_k=None, defer_enqueue=False):
         """
@@ -171,15 +250,11 @@ class MoCo(BaseMoCo):
         labels = self._labels(bsz, q.device)
         logits = self._fused_logits(q, k, self.memory, labels)
         if defer_enqueue:
-            if isinstance(logits, LazyLogits) and not self.track_overwritten:
-                logits._materialize = _stale_after_enqueue
+            self._arm_stale([logits])
             return logits, labels
         all_k = all_k if all_k is not None else k
-        if self.track_overwritten:
-            self._remember_overwritten([logits], self.memory, all_k.size(0))
-        elif isinstance(logits, LazyLogits):
-            logits._materialize = _stale_after_enqueue
         self.enqueue(all_k)
+        self._arm_stale([logits])
         return logits, labels
 
     def enqueue(self, all_k):
@@ -238,16 +313,19 @@ class MoCoAtt(BaseMoCo):
             logits = self._compute_logit_qk(q, k)
         elif torch.is_grad_enabled() and (k.requires_grad or queue.requires_grad):
             # the attended k / queue carry gradients into the attention parameters (the reference
-            # only detaches k *before* the attention, :116): keep full autograd on the dense form
+            # only detaches k *before* the attention, :116): keep full autograd on the dense form.
+            # autograd saves `queue` for backward and the enqueue below overwrites the live buffer
+            # behind its back -> copy it first (the reference's clone, :119)
+            if queue.data_ptr() == self.memory.data_ptr():
+                queue = queue.clone()
             logits = _dense_logits_autograd(q, k, queue, self.T)
         else:
             logits = self._fused_logits(q, k, queue.contiguous(), labels)
 
         all_k = all_k if all_k is not None else k
-        if isinstance(logits, LazyLogits):
-            logits._materialize = _stale_after_enqueue
         self._update_memory(all_k, self.memory)
         self._update_pointer(all_k.size(0))
+        self._arm_stale([logits])
         return logits, labels
 
 
@@ -271,12 +349,10 @@ class _DualQueue(BaseMoCo):
     def _finish(self, handles, k, k_t, all_k, all_k_t):
         all_k = all_k if all_k is not None else k
         all_k_t = all_k_t if all_k_t is not None else k_t
-        for h in handles:
-            if isinstance(h, LazyLogits):
-                h._materialize = _stale_after_enqueue
         self._update_memory(all_k, self.memory_s)
         self._update_memory(all_k_t, self.memory_t)
         self._update_pointer(all_k.size(0))
+        self._arm_stale(handles)
 
 
 class MoCoST(_DualQueue):

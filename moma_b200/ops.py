@@ -78,6 +78,9 @@ class EmaPlan:
 
 
 def plan_key(srcs, dsts) -> Tuple:
+    """The chunk table encodes exactly (source address, destination address, element count) per tensor, so this
+    key is the table's full content: a parameter re-allocated at the same address with the same element count
+    yields the same (still valid) table, any other change yields another key."""
     return tuple((s.data_ptr(), d.data_ptr(), d.numel()) for s, d in zip(srcs, dsts))
 
 
@@ -163,9 +166,10 @@ def pointer_advance(index_dev: torch.Tensor, n: int, K: int) -> None:
     check(_lib.load().moma_pointer_advance(_p(index_dev), int(n), int(K), _stream()))
 
 
-def enqueue_ids(n: int, index: int, K: int, device) -> torch.Tensor:
+def enqueue_ids(n: int, index: int, K: int, device, index_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ids = fmod(arange(n) + index, K).long()  (mem_moco.py:24-26); index read from the device mirror when given."""
     out = torch.empty(n, dtype=torch.int64, device=device)
-    check(_lib.load().moma_enqueue_ids(n, int(index), None, K, _p(out), _stream()))
+    check(_lib.load().moma_enqueue_ids(n, int(index), _p(index_dev), K, _p(out), _stream()))
     return out
 
 
@@ -331,11 +335,27 @@ def fused_nce_supported(D: int) -> bool:
     return D % 4 == 0 and D <= 512
 
 
+class QueueGuard:
+    """Rows of the queue that an enqueue overwrites between a dense-logits forward and its backward.
+
+    The dense path saves the LIVE queue for backward (no K x D clone per step, unlike mem_moco.py:89); the
+    enqueue kernel then overwrites n of its rows through a raw pointer, invisible to autograd's version
+    counter.  The module that runs the enqueue records (ids, old rows) here first; backward then computes
+    d loss/d q against the rows the logits were actually computed from."""
+    __slots__ = ("ids", "old")
+
+    def __init__(self):
+        self.ids, self.old = None, None
+
+    def remember(self, ids: torch.Tensor, old_rows: torch.Tensor) -> None:
+        self.ids, self.old = ids, old_rows
+
+
 class _NceLogits(torch.autograd.Function):
     """Dense logits [B, K+1] (mem_moco.py:29-49); backward = dense dlogits -> dq (k, queue detached)."""
 
     @staticmethod
-    def forward(ctx, q, k, queue, T):
+    def forward(ctx, q, k, queue, T, guard):
         q32, k32 = _f32c(q), _f32c(k)
         B, D = q32.shape
         K = queue.shape[0]
@@ -346,8 +366,11 @@ class _NceLogits(torch.autograd.Function):
         else:
             qo, ko = q32, k32
         check(_lib.load().moma_nce_logits(_p(qo), _p(ko), _p(queue), B, D, K, T, dtype, _p(out), _stream()))
-        ctx.save_for_backward(k32, queue)
-        ctx.T = T
+        if ctx.needs_input_grad[0]:
+            # without a guard the queue is copied (the reference's clone, mem_moco.py:89): the caller may
+            # overwrite it before backward runs
+            ctx.save_for_backward(k32, queue if guard is not None else queue.clone())
+        ctx.T, ctx.guard = T, guard
         return out
 
     @staticmethod
@@ -355,12 +378,19 @@ class _NceLogits(torch.autograd.Function):
         k32, queue = ctx.saved_tensors
         g = g / ctx.T
         dq = g[:, :1] * k32 + g[:, 1:] @ queue.float()      # escape hatch only: library GEMM
-        return dq, None, None, None
+        guard = ctx.guard
+        if guard is not None and guard.ids is not None:
+            # the enqueue replaced rows `ids` after the forward: swap their contribution for the old rows'
+            cols = g.index_select(1, guard.ids + 1)
+            dq = dq + cols @ (guard.old.float() - queue.index_select(0, guard.ids).float())
+        return dq, None, None, None, None
 
 
-def nce_logits(q, k, queue, T) -> torch.Tensor:
+def nce_logits(q, k, queue, T, guard: Optional[QueueGuard] = None) -> torch.Tensor:
+    """Dense logits.  ``guard``: see QueueGuard -- pass one (and fill it before the enqueue) to avoid the
+    queue copy that otherwise protects the backward from a later in-place queue update."""
     _need_cuda(q, k, queue)
-    return _NceLogits.apply(q, k.detach(), queue.detach(), float(T))
+    return _NceLogits.apply(q, k.detach(), queue.detach(), float(T), guard)
 
 
 def nce_logits_qk(q, k, T) -> torch.Tensor:
@@ -476,16 +506,21 @@ def attention_supported(C: int, H: int) -> bool:
 
 
 # -------------------------------------------------------------------------- projection-head Linear (+ReLU)
-_LINEAR_WS = {}
-
-
-def _linear_workspace(key, nbytes: int, device):
+def _linear_workspace(owner: torch.Tensor, key, nbytes: int, device):
     """Zeroed split-K workspace of one call site (a layer's forward or backward).  The kernels leave the ticket
-    counters zero, so it is zeroed exactly once; a call site never runs concurrently with itself."""
-    ws = _LINEAR_WS.get(key)
+    counters zero, so it is zeroed exactly once; a call site never runs concurrently with itself.  The workspace
+    lives ON the layer's weight tensor (attribute ``_moma_ws``), so its lifetime is the layer's: nothing is keyed by
+    ``id()`` / addresses that a later allocation could reuse."""
+    table = getattr(owner, "_moma_ws", None)
+    if table is None:
+        table = {}
+        try:
+            owner._moma_ws = table
+        except AttributeError:                      # exotic tensor subclass: fall back to a fresh workspace per call
+            return torch.zeros(max(nbytes, 16), dtype=torch.uint8, device=device)
+    ws = table.get(key)
     if ws is None or ws.numel() < nbytes or ws.device != device:
-        ws = torch.zeros(max(nbytes, 16), dtype=torch.uint8, device=device)
-        _LINEAR_WS[key] = ws
+        ws = table[key] = torch.zeros(max(nbytes, 16), dtype=torch.uint8, device=device)
     return ws
 
 
@@ -499,10 +534,10 @@ class _Linear(torch.autograd.Function):
         N = wc.shape[0]
         y = torch.empty((M, N), dtype=torch.float32, device=xc.device)
         nbytes = int(lib.moma_linear_workspace_bytes(M, N, K))
-        ws = _linear_workspace((key, "f", M, N, K), nbytes, xc.device)
+        ws = _linear_workspace(w, (key, "f", M, N, K), nbytes, xc.device)
         check(lib.moma_linear_fwd(_p(xc), _p(wc), _p(bc), M, N, K, int(relu), _p(y), _p(ws), nbytes, _stream()))
         ctx.save_for_backward(xc, wc, y if relu else None)
-        ctx.relu, ctx.key, ctx.has_b = bool(relu), key, b is not None
+        ctx.relu, ctx.key, ctx.has_b, ctx.owner = bool(relu), key, b is not None, w
         return y
 
     @staticmethod
@@ -517,7 +552,7 @@ class _Linear(torch.autograd.Function):
         gw = torch.empty_like(wc) if need[1] else None
         gb = torch.empty(N, dtype=torch.float32, device=xc.device) if (need[2] and ctx.has_b) else None
         nbytes = int(lib.moma_linear_workspace_bytes(M, N, K))
-        ws = _linear_workspace((ctx.key, "b", M, N, K), nbytes, xc.device)
+        ws = _linear_workspace(ctx.owner, (ctx.key, "b", M, N, K), nbytes, xc.device)
         check(lib.moma_linear_bwd(_p(xc), _p(wc), _p(y), _p(gy), M, N, K, int(ctx.relu), _p(gx), _p(gw), _p(gb),
                                   _p(ws), nbytes, _stream()))
         return gx, gw, gb, None, None
@@ -529,4 +564,4 @@ def linear(x, weight, bias=None, relu: bool = False, key=None):
     _need_cuda(x, weight)
     if x.dim() != 2 or weight.dim() != 2 or x.shape[1] != weight.shape[1]:
         raise RuntimeError(f"moma_b200.linear: bad shapes x {tuple(x.shape)} weight {tuple(weight.shape)}")
-    return _Linear.apply(x, weight, bias, bool(relu), key if key is not None else id(weight))
+    return _Linear.apply(x, weight, bias, bool(relu), key if key is not None else "linear")

@@ -78,7 +78,9 @@ class ShardedMoCo(BaseMoCo):
         return self.gather_full()
 
     def set_full(self, full: torch.Tensor) -> None:
-        self.memory_shard.copy_(cyclic_shard(full.to(self.memory_shard.device), self.rank, self.world))
+        with torch.no_grad():
+            self.memory_shard.copy_(cyclic_shard(full.to(self.memory_shard.device), self.rank, self.world))
+        self.invalidate_shadows()
 
     def broadcast_from_rank0(self) -> None:
         """ContrastTrainer.broadcast_memory for the sharded queue (reference :71-81)."""
@@ -87,15 +89,46 @@ class ShardedMoCo(BaseMoCo):
         dist.broadcast(full, 0, group=self.group)
         self.set_full(full)
 
+    # ---- checkpointing ------------------------------------------------------------------------------
+    # ``state_dict()`` is free of collectives (the usual ``if rank == 0: torch.save(contrast.state_dict())`` must not
+    # deadlock): it carries this rank's rows under 'memory_shard' plus the layout (rank, world) and the ring pointer.
+    # ``full_state_dict()`` is the explicit COLLECTIVE that presents the reference's key set ('memory' = full [K, D]).
+    # ``load_state_dict`` accepts either form.
     def _save_to_state_dict(self, destination, prefix, keep_vars):
         super()._save_to_state_dict(destination, prefix, keep_vars)
-        destination[prefix + "memory"] = self.gather_full()
+        destination[prefix + "memory_shard"] = self.memory_shard if keep_vars else self.memory_shard.detach()
+        destination[prefix + "shard_layout"] = torch.tensor([self.rank, self.world, int(self.index)], dtype=torch.int64)
 
-    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
-        key = prefix + "memory"
-        if key in state_dict:
-            self.set_full(state_dict.pop(key))
-        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+    def full_state_dict(self):
+        """COLLECTIVE (call on every rank): {'memory': full [K, D] fp32 queue in the reference's row order,
+        'index': ring pointer} -- loadable by MoCo, by ShardedMoCo of any world size, and ('memory' alone) by
+        the reference's MoCo."""
+        return {"memory": self.gather_full(), "index": torch.tensor(int(self.index), dtype=torch.int64)}
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                              error_msgs):
+        full, shard, layout = prefix + "memory", prefix + "memory_shard", prefix + "shard_layout"
+        if full in state_dict:
+            self.set_full(state_dict.pop(full))
+            state_dict.pop(shard, None)
+            state_dict.pop(layout, None)
+        elif shard in state_dict:
+            lay = state_dict.pop(layout, None)
+            if lay is not None:
+                r, w, idx = (int(v) for v in lay)
+                if (r, w) != (self.rank, self.world):
+                    error_msgs.append(f"ShardedMoCo: checkpoint shard is rank {r} of {w}, this process is rank "
+                                      f"{self.rank} of {self.world} (save with full_state_dict() to re-shard)")
+                    state_dict.pop(shard)
+                    return
+                self.index = idx % self.K
+                if self._index_dev is not None:
+                    self._index_dev.fill_(self.index)
+            self.memory_shard.copy_(state_dict.pop(shard).to(self.memory_shard.device))
+        elif strict:
+            missing_keys.append(shard)
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                                      error_msgs)
 
     # ---- exchange of the per-rank partials ------------------------------------------------------
     def _exchange(self, packed: torch.Tensor) -> torch.Tensor:

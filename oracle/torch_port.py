@@ -1,4 +1,4 @@
-"""torch (CPU) port of the reference's MoMA criterion step -- TEST / BASELINE INFRASTRUCTURE ONLY.
+"""torch port of the reference's MoMA criterion step -- TEST / BASELINE INFRASTRUCTURE ONLY.
 
 This is the CPU arm that bench.py times (``cpu_baseline.kind = "port"`` and
 ``--impl reference``): the reference's own op sequence on its own arithmetic type
@@ -55,24 +55,40 @@ def port_head(in_dim, feat_dim):
 
 
 class PortMoCo(nn.Module):
-    """mem_moco.py:69-100"""
+    """mem_moco.py:69-100.  ``operand_dtype`` (GPU baseline arm only): dtype of the q / queue operands of the
+    negatives GEMM -- torch.bfloat16 is "the reference with bf16 operands" of SURVEY 8d(iii): the library
+    (cuBLAS sm_100) tensor-core GEMM the fused kernel has to beat; None = the reference's fp32."""
 
-    def __init__(self, n_dim, K, T):
+    def __init__(self, n_dim, K, T, operand_dtype=None):
         super().__init__()
         self.K, self.T, self.index = K, T, 0
+        self.operand_dtype = operand_dtype
+        self.device_constants = False     # True (graph-captured GPU arm): labels / ids are created on the device --
+                                          # a capture cannot contain the reference's per-step pageable H2D copies
         self.register_buffer("memory", F.normalize(torch.randn(K, n_dim)))
 
     def forward(self, q, k, all_k=None):
         bsz = q.size(0)
+        dev = q.device
         k = k.detach()
         queue = self.memory.clone().detach()                              # :89
         pos = torch.bmm(q.view(bsz, 1, -1), k.view(bsz, -1, 1)).view(bsz, 1)    # :38-39
-        neg = torch.mm(queue, q.transpose(1, 0)).transpose(0, 1)          # :42-43
+        if self.operand_dtype is None:
+            neg = torch.mm(queue, q.transpose(1, 0)).transpose(0, 1)      # :42-43
+        else:
+            od = self.operand_dtype
+            neg = torch.mm(queue.to(od), q.to(od).transpose(1, 0)).transpose(0, 1).float()
         out = torch.div(torch.cat((pos, neg), dim=1), self.T).squeeze().contiguous()   # :45-47
-        labels = torch.zeros(bsz, dtype=torch.long)                       # :94
+        if self.device_constants:
+            labels = torch.zeros(bsz, dtype=torch.long, device=dev)
+        else:
+            labels = torch.zeros(bsz, dtype=torch.long).to(dev)           # :94 (CPU tensor, then .cuda())
         all_k = all_k if all_k is not None else k
         with torch.no_grad():                                             # :23-27
-            ids = torch.fmod(torch.arange(all_k.shape[0]) + self.index, self.K).long()
+            if self.device_constants:
+                ids = torch.fmod(torch.arange(all_k.shape[0], device=dev) + self.index, self.K).long()
+            else:
+                ids = torch.fmod(torch.arange(all_k.shape[0]) + self.index, self.K).long().to(dev)
             self.memory.index_copy_(0, ids, all_k)
         self.index = (self.index + all_k.size(0)) % self.K                # :14-15
         return out, labels
@@ -95,17 +111,21 @@ def port_momentum_update(params, params_ema, m):
 class PortCriterionStep:
     """One criterion step on CPU with the reference's op sequence (L1 of SURVEY 8d)."""
 
-    def __init__(self, s_dim, t_dim, feat_dim, K, T, alpha, num_heads, ema_shapes, seed=12345):
+    def __init__(self, s_dim, t_dim, feat_dim, K, T, alpha, num_heads, ema_shapes, seed=12345, device="cpu",
+                 operand_dtype=None):
+        """device='cpu': the CPU arm (the default, what --impl reference times).  device='cuda': the same op
+        sequence executed by the stock PyTorch/ATen/cuBLAS GPU kernels -- the reference's own GPU behaviour,
+        timed by bench.py beside the repo's kernels (``gpu_reference``); never part of the product path."""
         torch.manual_seed(seed)
-        self.contrast = PortMoCo(feat_dim, K, T)
-        self.embed_s = port_head(s_dim, feat_dim)
-        self.embed_t = port_head(t_dim, feat_dim)
-        self.atts_q = PortAttention(feat_dim, num_heads)
-        self.atts_k = PortAttention(feat_dim, num_heads)
-        self.atts_queue = PortAttention(feat_dim, num_heads)
+        self.contrast = PortMoCo(feat_dim, K, T, operand_dtype).to(device)
+        self.embed_s = port_head(s_dim, feat_dim).to(device)
+        self.embed_t = port_head(t_dim, feat_dim).to(device)
+        self.atts_q = PortAttention(feat_dim, num_heads).to(device)
+        self.atts_k = PortAttention(feat_dim, num_heads).to(device)
+        self.atts_queue = PortAttention(feat_dim, num_heads).to(device)
         self.alpha = alpha
-        self.student = [torch.randn(*s) for s in ema_shapes]
-        self.teacher = [torch.randn(*s) for s in ema_shapes]
+        self.student = [torch.randn(*s).to(device) for s in ema_shapes]
+        self.teacher = [torch.randn(*s).to(device) for s in ema_shapes]
         self.head_ema = s_dim == t_dim
         self.ce = nn.CrossEntropyLoss()
 

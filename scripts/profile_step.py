@@ -3,7 +3,8 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from torch.profiler import ProfilerActivity, profile
-from bench import CONFIGS, CriterionStep
+from bench import CONFIGS
+from moma_b200.step import CriterionStep
 from moma_b200.graphed import GraphedStep
 
 cfg = CONFIGS[sys.argv[1] if len(sys.argv) > 1 else "C2"]

@@ -3,7 +3,8 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
-from bench import CONFIGS, CriterionStep
+from bench import CONFIGS
+from moma_b200.step import CriterionStep
 
 cfg = CONFIGS[sys.argv[1] if len(sys.argv) > 1 else "C2"]
 dev = torch.device("cuda", 0)

@@ -2,7 +2,8 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from bench import CONFIGS, CriterionStep
+from bench import CONFIGS
+from moma_b200.step import CriterionStep
 
 def run(cfg, tf32, precision):
     import moma_b200

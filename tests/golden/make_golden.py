@@ -277,6 +277,118 @@ def kat_gloo():
     save("kat_gloo", **out)
 
 
+# ------------------------------------------------- MoCoAtt: every attention mode
+MOCOATT_MODES = [("all", "all"), ("qk", "qk"), ("dual", "dual"), ("dual2", "dual2"), ("self_qk", "self_qk"),
+                 ("self", "self")]           # (CMO opt.attn, MoCoAtt.forward attn=)
+
+
+def kat_mocoatt():
+    """MoMA/mem_moco.py:111-161 with the CMO attention set each mode needs (criterion_moco_att.py:308-338).
+    Small K because 'all' / 'dual' / 'self' attend the whole queue (N = K tokens)."""
+    from MoMA.mem_moco import MoCoAtt
+    out = {}
+    D, K, B, T = 32, 24, 6, 0.15
+    for opt_attn, mode in MOCOATT_MODES:
+        torch.manual_seed(500 + len(mode))
+        opt = Namespace(head="linear", s_dim=8, t_dim=8, feat_dim=D, attn=opt_attn)
+        crit = CMO(opt)
+        m = MoCoAtt(D, K, T)
+        m.index = 20                                   # wraps: rows 20..23, 0..1
+        q = torch.randn(B, D).requires_grad_()
+        k = torch.randn(B, D)
+        mem0 = m.memory.clone()
+        logits, labels = m(q, k, attn=mode, criterion_kd=crit)
+        if mode == "dual2":
+            loss = logits.sum()                        # [B] positives only (:51-66): no CE over one column
+        else:
+            loss = nn.CrossEntropyLoss()(logits, labels)
+        loss.backward()
+        tag = f"{mode}_"
+        out.update({tag + "q": npy(q), tag + "k": npy(k), tag + "mem0": npy(mem0), tag + "logits": npy(logits),
+                    tag + "loss": np.float32(loss.item()), tag + "dq": npy(q.grad), tag + "mem1": npy(m.memory),
+                    tag + "index": np.int64(m.index)})
+        for n, p_ in crit.state_dict().items():
+            out[tag + "sd_" + n] = npy(p_)
+        for n, p_ in crit.named_parameters():
+            out[tag + "hasgrad_" + n] = np.bool_(p_.grad is not None)
+            if p_.grad is not None:
+                out[tag + "grad_" + n] = npy(p_.grad)
+    save("kat_mocoatt", **out)
+
+
+# ------------------------------------------------- projection heads other than 'mlp'
+def kat_heads():
+    """criterion_moco_att.py:269-305: 'mlp_byol' (train-mode BatchNorm1d), 'linear', and the bare Normalize head."""
+    out = {}
+    for head in ("mlp_byol", "linear", "none"):
+        torch.manual_seed(700 + len(head))
+        opt = Namespace(head=head, s_dim=20, t_dim=12, feat_dim=16, attn="self")
+        crit = CMO(opt)
+        x = torch.randn(10, 20 if head != "none" else 16).requires_grad_()
+        for n, p_ in crit.embed_s.state_dict().items():
+            out[f"{head}_sd0_{n}"] = npy(p_)
+        y = crit.embed_s(x)
+        g = torch.randn_like(y)
+        y.backward(g)
+        out.update({f"{head}_x": npy(x), f"{head}_y": npy(y), f"{head}_g": npy(g), f"{head}_dx": npy(x.grad)})
+        for n, p_ in crit.embed_s.named_parameters():
+            out[f"{head}_grad_{n}"] = npy(p_.grad)
+        for n, p_ in crit.embed_s.state_dict().items():
+            out[f"{head}_sd1_{n}"] = npy(p_)            # BatchNorm running stats after the train-mode forward
+    save("kat_heads", **out)
+
+
+# ------------------------------------- 2-rank gloo: ShuffleBN (contrast_trainer.py:90-133)
+class TinyTeacher(nn.Module):
+    """Stand-in momentum encoder with the (feats, logit) = model(x, is_feat=True) convention of the reference
+    backbones; BatchNorm in train mode makes the output depend on WHICH samples share a device -- exactly what
+    ShuffleBN permutes."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv = nn.Conv2d(3, 5, 3, padding=1)
+        self.bn = nn.BatchNorm2d(5)
+        self.fc = nn.Linear(5, 4)
+
+    def forward(self, x, is_feat=False):
+        f = torch.relu(self.bn(self.conv(x))).mean(dim=(2, 3))
+        logit = self.fc(f)
+        return ([f], logit) if is_feat else logit
+
+
+def _shufflebn_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", world_size=world, rank=rank)
+    args = Namespace(local_rank=rank, node_rank=0, ngpus_per_node=world, rank=rank, mem="MoCo")
+    tr = ContrastTrainer(args)
+    tr.local_group = dist.new_group(ranks=list(range(world)), backend="gloo")
+    torch.manual_seed(321)                        # same weights on every rank
+    teacher = TinyTeacher().train()
+    head = nn.Sequential(nn.Linear(5, 8), Normalize(2))
+    torch.manual_seed(400 + rank)
+    x = torch.randn(6, 3, 4, 4)
+    torch.manual_seed(77)                         # the permutation is rank 0's draw (broadcast), seeded here
+    k, all_k = tr._shuffle_bn(x, teacher, head)
+    ret[rank] = dict(x=npy(x), k=npy(k), all_k=npy(all_k),
+                     bn_mean=npy(teacher.bn.running_mean), bn_var=npy(teacher.bn.running_var))
+    dist.barrier(); dist.destroy_process_group()
+
+
+def kat_shufflebn():
+    import torch.multiprocessing as mp
+    mgr = mp.Manager(); ret = mgr.dict()
+    mp.spawn(_shufflebn_worker, args=(2, 29613, ret), nprocs=2, join=True)
+    out = {}
+    for r in (0, 1):
+        for key, v in ret[r].items():
+            out[f"r{r}_{key}"] = np.asarray(v)
+    save("kat_shufflebn", **out)
+
+
 if __name__ == "__main__":
-    kat_moco(); kat_pointer(); kat_attention(); kat_normalize(); kat_ema()
-    criterion_step(); kat_dual(); kat_gloo()
+    only = sys.argv[1:]
+    for fn in (kat_moco, kat_pointer, kat_attention, kat_normalize, kat_ema, criterion_step, kat_dual, kat_gloo,
+               kat_mocoatt, kat_heads, kat_shufflebn):
+        if not only or fn.__name__ in only:
+            fn()

@@ -86,14 +86,22 @@ def _worker(rank, world, port, ret):
     losses, accs = ContrastTrainer._compute_loss_accuracy([logits], labels, torch.nn.CrossEntropyLoss())
     losses[0].backward()
     m.enqueue(all_k=all_k)
-    sd = m.state_dict()                                       # collective: gathers the full queue
+    # state_dict() is collective-free (a rank-0-only save must not deadlock): only rank 0 calls it here
+    local_keys = []
+    if rank == 0:
+        sd_local = m.state_dict()
+        local_keys = list(sd_local.keys())
+        m3 = ShardedMoCo(16, 32, 0.15)
+        m3.load_state_dict(sd_local)                          # per-rank shard + pointer round trip
+        assert torch.equal(m3.memory_shard, m.memory_shard) and m3.index == m.index
+    sd = m.full_state_dict()                                  # explicit collective: the reference's key set + pointer
     ret[rank] = dict(mem0=mem0.numpy(), mem1=sd["memory"].numpy(), index=m.index, loss=losses[0].item(),
                      acc=accs[0].item(), dq=q.grad.numpy(), all_k=all_k.numpy(), shape=tuple(logits.shape),
-                     shard=m.memory_shard.numpy().copy(), keys=list(sd.keys()))
-    # load_state_dict scatters the full queue back into shards
+                     shard=m.memory_shard.numpy().copy(), keys=list(sd.keys()), local_keys=local_keys)
+    # load_state_dict scatters the full queue back into shards and restores the pointer
     m2 = ShardedMoCo(16, 32, 0.15)
     m2.load_state_dict(sd)
-    assert torch.equal(m2.memory_shard, m.memory_shard)
+    assert torch.equal(m2.memory_shard, m.memory_shard) and m2.index == m.index == 4
     dist.barrier(); dist.destroy_process_group()
 
 
@@ -118,3 +126,4 @@ def test_sharded_queue_matches_reference_two_rank_run(golden):
         assert out["index"] == int(g[f"r{r}_index"]) == 4
         assert np.array_equal(out["shard"], g[f"r{r}_mem1"][r::2])         # cyclic ownership
         assert "memory" in out["keys"] and "memory_shard" not in out["keys"]
+    assert "memory_shard" in ret[0]["local_keys"] and "memory" not in ret[0]["local_keys"]
