@@ -562,6 +562,17 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mt = blockIdx.x, split = blockIdx.y;
+    // life-cycle trace (hooked build, bit 1024): clock64 stamps of the first and the last CTA of the grid
+    long long* life = nullptr;
+    if (kAblateHooks && (ablate & 1024) && dbg_S != nullptr) {
+        const bool first = mt == 0 && split == 0, last = mt == (int)gridDim.x - 1 && split == (int)gridDim.y - 1;
+        if (first || last) life = reinterpret_cast<long long*>(dbg_S + 2ll * B * 128) + 4096 + (last ? 32 : 0);
+    }
+#define LIFE(k) do { if (life) life[k] = clock64(); } while (0)
+    if (life && threadIdx.x == 0) {
+        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        life[0] = clock64(); life[20] = (long long)gt;
+    }
     const int T_total = (int)((K_local + BN - 1) / BN);
     const int t0 = (int)((long long)T_total * split / n_splits);
     const int t1 = (int)((long long)T_total * (split + 1) / n_splits);
@@ -609,8 +620,10 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
     auto s_colf = [&](int b) { return tmem + (uint32_t)(b * 128); };
+    if (threadIdx.x == 0) LIFE(1);
     // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the tail of the preceding kernel
     pdl_wait();
+    if (threadIdx.x == 0) LIFE(2);
 
     if (warp == 0) {
         // ===================================================== TMA producer
@@ -625,6 +638,7 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 mbar_expect_tx(b_kv_full(s), C::K_TILE);
                 for (int kb = 0; kb < C::KB; ++kb)
                     tma_load_2d(kv_smem + s * C::K_TILE + kb * C::K_BLOCK, &tmap_k, kb * 64, (t0 + i) * BN, b_kv_full(s));
+                if (i == 0) LIFE(3);
             }
         }
     } else if (warp == 1) {
@@ -656,7 +670,9 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             mbar_wait(b_q_full, 0, 302);
             mbar_wait(b_kv_full(0), 0, 303);
             tc_fence_after();
+            LIFE(4);
             issue_s(0, 0);
+            LIFE(5);
             for (int j = 1; j < kSBuf && j < nt; ++j) { mbar_wait(b_kv_full(j), 0, 306); tc_fence_after(); issue_s(j, j); }
             long long* tr = ((ablate & 256) && dbg_S != nullptr && mt == 0 && split == 0)
                                 ? reinterpret_cast<long long*>(dbg_S + 2ll * B * 128) : nullptr;
@@ -683,6 +699,8 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             }
 #undef IS_STAMP
             umma_commit(b_o_final);
+            LIFE(8);
+            if (life) life[12] = nt;
             if (tr) { tr[1] = clock64(); tr[2] = nt; }
         }
     } else if (warp >= 4) {
@@ -706,6 +724,7 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             SM_STAMP(0);
             mbar_wait(b_s_full(b), (i / kSBuf) & 1, 401);
             tc_fence_after();
+            if (i == 0 && warp == 4 && lane == 0) LIFE(6);
             SM_STAMP(1);
             uint32_t v[64];
             if (ablate & 2) {
@@ -788,6 +807,7 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             __syncwarp();
             SM_STAMP(5);
             if (lane == 0) mbar_arrive(b_p_full(b));          // one arrival per warp: 8 instead of 256 smem atomics
+            if (i == 0 && warp == 4 && lane == 0) LIFE(7);
             SM_STAMP(6);
         }
 #undef SM_STAMP
@@ -798,6 +818,7 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         if (half == 1) bars->lsum[rit] = l_half;
         mbar_wait(b_o_final, 0, 403);
         tc_fence_after();
+        if (warp == 4 && lane == 0) LIFE(9);
         const long long orow = (long long)split * B + row;
 #pragma unroll 1
         for (int c = 0; c < C::OH / 32; ++c) {
@@ -819,11 +840,17 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             part_mmax[orow] = m_true * kLn2;
             part_l[orow] = l_half + bars->lsum[rit];
         }
+        if (warp == 4 && lane == 0) LIFE(10);
     }
 
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem, kTmemCols);
+    if (life && threadIdx.x == 0) {
+        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        life[11] = clock64(); life[21] = (long long)gt;
+    }
+#undef LIFE
 }
 
 // ----------------------------------------------------------------------------- host side

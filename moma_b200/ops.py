@@ -394,11 +394,12 @@ def nce_logits(q, k, queue, T, guard: Optional[QueueGuard] = None) -> torch.Tens
 
 
 def nce_logits_qk(q, k, T) -> torch.Tensor:
-    """mem_moco.py:51-66; tiny, differentiable through torch ops on the kernel's operands."""
+    """mem_moco.py:51-66 (positives only, [B]).  Tiny; when either operand carries gradients (MoCoAtt 'dual2': the
+    attended k is NOT detached in the reference, :116 detaches before the attention) it stays on autograd ops."""
     _need_cuda(q, k)
-    q32, k32 = _f32c(q), _f32c(k.detach())
-    if q.requires_grad and torch.is_grad_enabled():
-        return (q32 * k32).sum(1) / T
+    if torch.is_grad_enabled() and (q.requires_grad or k.requires_grad):
+        return (_f32c(q) * _f32c(k)).sum(1) / T
+    q32, k32 = _f32c(q.detach()), _f32c(k.detach())
     out = torch.empty(q32.shape[0], dtype=torch.float32, device=q.device)
     check(_lib.load().moma_nce_logits_qk(_p(q32), _p(k32), q32.shape[0], q32.shape[1], float(T), _p(out), _stream()))
     return out
