@@ -250,7 +250,7 @@ def build_and_check(ctx: Ctx, cfg, sharded, oracle=True):
 
 # ----------------------------------------------------------------------------- kernel shares (CUPTI)
 FAMILIES = [
-    ("nce_tc", r"nce_tc2?_kernel"),
+    ("nce_tc", r"nce_tc\d?_kernel"),
     ("nce_combine", r"nce_reduce_kernel|nce_finalize_kernel"),
     ("gemm3xtf32", r"gemm3xtf32_kernel"),
     ("colsum", r"colsum"),
@@ -288,7 +288,9 @@ def kernel_shares(ctx: Ctx, graphed, replays=5):
         key = next((f for f, pat in FAMILIES if re.search(pat, name)), None)
         if key is None:
             key = "other"
-            other[name[:60]] = other.get(name[:60], 0) + 1
+            o = other.setdefault(name[:70], {"us": 0.0, "launches": 0.0})
+            o["us"] = round(o["us"] + e.duration_ns() / 1e3 / replays, 2)
+            o["launches"] = round(o["launches"] + 1.0 / replays, 1)
         d = fam.setdefault(key, {"us": 0.0, "launches": 0})
         d["us"] += e.duration_ns() / 1e3 / replays
         d["launches"] += 1.0 / replays
@@ -383,8 +385,20 @@ def measure(ctx: Ctx, name, cfg, steps, strong=False, full=False):
                   "path": "pinned host features -> H2D on a copy stream (double-buffered, overlapping the previous step) -> "
                           "static device buffers, graph replay, loss.item()"}
 
-    # ---- per-kernel: shares of the step (CUPTI) + isolated cold timings for the two north-star kernels
-    fam, other, err = kernel_shares(ctx, graphed)
+    # ---- per-kernel: shares of the step (CUPTI) + isolated cold timings for the two north-star kernels.  A kernel
+    #      launched with programmatic dependent launch starts early and waits for its predecessor inside its own
+    #      "duration", so the shares come from a SECOND capture of the same step with PDL off (never timed as `value`)
+    from moma_b200.graphed import GraphedStep
+    was = lib.moma_debug_set_pdl(0)
+    try:
+        g_nopdl = GraphedStep(cs.step_overlapped, contrast=cs.contrast, rows_per_step=n, warmup=1)
+        for _ in range(2):
+            g_nopdl.replay()
+        out["ms_per_step_without_pdl"] = ctx.timed(g_nopdl.replay, max(20, steps // 5)) / max(20, steps // 5)
+        fam, other, err = kernel_shares(ctx, g_nopdl)
+        del g_nopdl
+    finally:
+        lib.moma_debug_set_pdl(was)
     from moma_b200._lib import BF16
     plan = ops._EMA_PLANS[ops.plan_key([p.detach() for p in cs.student], [p.detach() for p in cs.teacher])]
     ema_us = ctx.kernel_us(lambda: plan.run(ALPHA))
@@ -398,8 +412,10 @@ def measure(ctx: Ctx, name, cfg, steps, strong=False, full=False):
         st_buf[1].data_ptr(), st_buf[2].data_ptr(), o_buf.data_ptr(), torch.cuda.current_stream().cuda_stream)))
     out["rooflines"] = rooflines(ctx, name, cfg, cs, fam, nce_us, ema_us, gemm_flop, attn_flop, n_splits)
     out["kernel_shares"] = {"families": fam, "unmatched": other, "error": err,
-                            "how": "CUPTI activity records (torch.profiler) of graph replays with the L2 flushed before each; "
-                                   "mean per replay; kernels on parallel branches overlap, so the sum exceeds the step time"}
+                            "how": "CUPTI activity records (torch.profiler) of replays of a capture of the same step made with "
+                                   "programmatic dependent launch OFF (with it a kernel's record includes its wait for the "
+                                   "predecessor), L2 flushed before each replay; mean per replay; kernels on parallel "
+                                   "branches overlap, so the sum exceeds the step time"}
     return out, cs, graphed
 
 
@@ -450,8 +466,8 @@ def rooflines(ctx, name, cfg, cs, fam, nce_us, ema_us, gemm_flop, attn_flop, n_s
         return e
 
     entries = [
-        tensor_entry("nce_tc2_kernel (tcgen05 InfoNCE logits + CE forward/backward)", "nce_tc", nce_flop, nce_us,
-                     {"traffic": traffic.get("nce_tc2_kernel"), "splits": n_splits,
+        tensor_entry("nce_tc3_kernel (tcgen05 InfoNCE logits + CE forward/backward)", "nce_tc", nce_flop, nce_us,
+                     {"traffic": traffic.get("nce_tc3_kernel", traffic.get("nce_tc2_kernel")), "splits": n_splits,
                       "timing": "achieved/frac: one launch alone, cold L2 (256 MiB flush read before it), CUDA events, "
                                 "median of 20; *_in_step: the same kernel inside the replayed step (CUPTI)"}),
         tensor_entry("gemm3xtf32_kernel (projection heads + attention projections, 3xTF32 mma.sync)", "gemm3xtf32",
@@ -582,7 +598,7 @@ def run_ours(args, rank, world, local_rank):
         return main, 3
 
     roofs = main.pop("rooflines")
-    north = next((r for r in roofs if r["kernel"].startswith("nce_tc2")), None)
+    north = next((r for r in roofs if r["kernel"].startswith("nce_tc")), None)
     cfg = CONFIGS[name]
     out = {
         "metric": "MoMA criterion samples/sec", "value": main["value"], "unit": "samples/s", "n_gpus": world,

@@ -266,6 +266,10 @@ long long moma_debug_launch_count(int reset);
  * kind 0 = Linear GEMMs of moma_linear_* / the attention projections (2*M*N*K each, counted once although the
  * 3xTF32 kernel runs three tensor-core passes), kind 1 = attention core (forward 4*Nq*N*C, backward 8*N*N*C). */
 double moma_debug_flops(int kind, int reset);
+/* Turn programmatic dependent launch on / off for subsequent launches (returns the previous setting).  A kernel
+ * launched with the attribute starts while its predecessor drains and then waits, so profiler "durations" include
+ * that wait: bench.py captures a second graph with PDL off to measure per-kernel shares. */
+int moma_debug_set_pdl(int enable);
 
 #ifdef __cplusplus
 }

@@ -47,9 +47,15 @@ int fail(int code, const char* fmt, ...) {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
     return code;
 }
+static std::atomic<int> g_pdl{-1};     // -1: not decided yet (MOMA_B200_PDL read on first use), else 0 / 1
 bool pdl_enabled() {
-    static const bool on = [] { const char* e = getenv("MOMA_B200_PDL"); return !(e != nullptr && e[0] == '0'); }();
-    return on;
+    int v = g_pdl.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("MOMA_B200_PDL");
+        v = !(e != nullptr && e[0] == '0');
+        g_pdl.store(v, std::memory_order_relaxed);
+    }
+    return v != 0;
 }
 bool use_simt_gemm() {
     static const bool simt = [] { const char* e = getenv("MOMA_B200_GEMM"); return e != nullptr && std::string(e) == "simt"; }();
@@ -71,6 +77,11 @@ int sm_count() {
 
 extern "C" __attribute__((visibility("default"))) long long moma_debug_launch_count(int reset) {
     return reset ? moma::g_launches.exchange(0) : moma::g_launches.load();
+}
+extern "C" __attribute__((visibility("default"))) int moma_debug_set_pdl(int enable) {
+    const bool was = moma::pdl_enabled();
+    moma::g_pdl.store(enable ? 1 : 0, std::memory_order_relaxed);
+    return was ? 1 : 0;
 }
 extern "C" __attribute__((visibility("default"))) double moma_debug_flops(int kind, int reset) {
     if (kind < 0 || kind >= 4) return 0.0;

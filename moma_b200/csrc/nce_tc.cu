@@ -15,6 +15,8 @@
 //   warp 1      MMA issuer (one elected lane issues every tcgen05.mma / tcgen05.commit)
 //   warp 2      TMEM allocator (512 columns)
 //   warps 4-7   softmax group 0, warps 8-11 softmax group 1 (one thread per query row)
+// (This header describes the first-generation kernel nce_tc_kernel, still used for D = 256; D = 64 / 128 run the
+//  v3 kernel further down, which documents its own layout.)
 // Two schedules share the code (template NQ):
 //   NQ = 2 (D <= 128, B > 128): two 128-row query tiles per CTA ping-pong, so the tensor pipe
 //           works on tile B while the softmax group of tile A is busy (TMEM: S0 S1 O0 O1).
@@ -471,17 +473,25 @@ nce_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     if (warp == 2) tmem_dealloc(tmem, kTmemCols);
 }
 
-// ============================================================================= v2 kernel
-// One 128-row query tile per CTA; the score tile S is triple-buffered in TMEM (S0 S1 S2 O = 512 columns at
-// D = 128) so the tensor pipe has S(i+1), S(i+2) finished while the softmax of tile i is in flight, and the softmax of each tile is split by
-// COLUMNS over two warpgroups (8 warps, two per scheduler, 64 columns per thread):
-//   warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
+// ============================================================================= v3 kernel (D = 64, 128)
+// One 128-row query tile per CTA; the score tile S is triple-buffered in TMEM (S0 S1 S2 O = 512 columns at D = 128)
+// so the tensor pipe has S(i+1), S(i+2) finished while the softmax of tile i is in flight.  Roles:
+//   warp 0 TMA producer (starts loading before the CTA-wide set-up barrier), warp 1 MMA issuer, warp 2 TMEM allocator,
 //   warps 4-7   softmax half 0 (score columns  0..63, O columns 0..D/2),
 //   warps 8-11  softmax half 1 (score columns 64..127, O columns D/2..D).
-// The two threads that share a row exchange their half-row maxima through shared memory and a
-// 64-thread named barrier, which also orders "partner has read S" before P (aliasing S) is written.
-// Scale / sum use packed f32x2 instructions; an FMA-pipe polynomial exp2 (ex2_poly) is available behind
-// kPolyExp for when the MUFU pipe (16 exp2/clk/SM: 128x128 exps vs 2 x 128x128x128 MACs per tile) becomes the limit.
+// What changed against the round-1 kernel (measured there: 2200 clk per tile, softmax 1940 clk with the MUFU pipe idle
+// during its tcgen05.ld / row-max phases, 2.9 us epilogue):
+//   * STREAMING softmax: the lazy reference max means P = exp2(S*c - m_ref) does not need this tile's row max, so each
+//     32-column chunk goes tcgen05.ld -> scale -> exp2 -> sum -> pack while the next chunk's load is in flight and the
+//     other warp of the scheduler keeps the MUFU pipe busy; the row max is only CHECKED at the end of the tile (half-row
+//     maxima exchanged through shared memory + a 64-thread named barrier) and the rare tile whose max outgrows the
+//     reference by 2^20 (always the first) recomputes its P from the score registers it still holds.
+//   * P is written over the half's OWN score columns ([64h, 64h + 32)), so the two halves never wait for each other
+//     to have read S; the PV MMAs take their A operand from those two column ranges.
+//   * one tcgen05.commit less per tile: PV(i) commits pv_done[i % stages], which both frees the shared-memory stage for
+//     the producer and orders O for a rescale (no separate "stage empty" commit).
+//   * epilogue through shared memory: O (TMEM) is staged in the (now idle) queue-tile ring with a padded row stride and
+//     written out with fully coalesced 128-bit stores (was: one scattered 16-byte store per row per instruction).
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     uint64_t d;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d)
@@ -504,80 +514,116 @@ __device__ __forceinline__ float ex2_poly(float x) {
     float p = fmaf(f, 0.0551716685f, 0.2426111251f);
     p = fmaf(p, f, 0.6932609677f);
     p = fmaf(p, f, 0.9999280572f);
-    return __int_as_float(__float_as_int(p) + ((__float_as_int(t) - 0x4B400000) << 23));
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));   // (t - magic) << 23: magic's bits shift out
 }
-// Measured on B200 (profiles/): with 8 softmax warps the kernel is issue/latency-bound, not MUFU-bound
-// (XU pipe ~31% busy), and the 9-instruction polynomial costs more issue slots than the MUFU op it saves.
-constexpr bool kPolyExp = false;
 __device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void group_barrier(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+// tcgen05.wait::ld that also "produces" the registers of the load it waits for, so the compiler cannot move their
+// first use above the wait (the load's own asm statement only says the registers are written)
+#define TMEM_WAIT_LD32(r)                                                                                \
+    asm volatile("tcgen05.wait::ld.sync.aligned;"                                                        \
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]),   \
+                   "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]),            \
+                   "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),         \
+                   "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),         \
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]),         \
+                   "+r"(r[31]) :: "memory")
 
 #ifdef MOMA_TC_ABLATE
 constexpr bool kAblateHooks = true;
 #else
 constexpr bool kAblateHooks = false;
 #endif
-constexpr int kStages2 = 5;     // queue-tile ring depth of the v2 kernel
+constexpr int kStages3 = 5;     // queue-tile ring depth
 constexpr int kSBuf = 3;        // score buffers in TMEM: S(i+1), S(i+2) are ready while softmax works on S(i)
 
-struct __align__(8) Bars2 {
+struct __align__(16) Bars3 {
     uint64_t q_full;
-    uint64_t kv_full[kStages2];
-    uint64_t kv_empty[kStages2];
+    uint64_t kv_full[kStages3];
     uint64_t s_full[kSBuf];
     uint64_t p_full[kSBuf];
-    uint64_t pv_done[kSBuf];   // PV(i) commits pv_done[i % kSBuf]: a waiter is never more than one phase behind
+    uint64_t pv_done[kStages3];  // PV(i) commits pv_done[i % kStages3]; its next completion needs tile i + kStages3 loaded,
+                                 // i.e. the producer to have seen this one: a waiter is never more than one phase behind
     uint64_t o_final;
     uint32_t tmem_base;
     uint32_t pad;
-    float xch[2][2][kBM];      // [tile parity][half][row] half-row maxima
-    float lsum[kBM];           // half-1 row sums for the epilogue
+    float xch[2][2][kBM];        // [tile parity][half][row] half-row maxima
+    float lsum[kBM];             // half-1 row sums for the epilogue
 };
 
 template <int D>
-struct Cfg2 {
+struct Cfg3 {
     static constexpr int BN = 128;
     static constexpr int KB = D / 64;
     static constexpr int Q_BLOCK = kBM * 128;
     static constexpr int Q_TILE = KB * Q_BLOCK;
     static constexpr int K_BLOCK = BN * 128;
     static constexpr int K_TILE = KB * K_BLOCK;
-    static constexpr int SMEM_DATA = Q_TILE + kStages2 * K_TILE;
-    static constexpr int SMEM_TOTAL = SMEM_DATA + 1024 + (int)sizeof(Bars2);
+    static constexpr int SMEM_DATA = Q_TILE + kStages3 * K_TILE;
+    static constexpr int SMEM_TOTAL = SMEM_DATA + 1024 + (int)sizeof(Bars3);
     static constexpr int THREADS = 384;
     static constexpr int O_COL = 128 * kSBuf;
     static constexpr int OH = D / 2;          // O columns per softmax half
+    static constexpr int STAGE_LD = D + 4;    // padded row stride (floats) of the epilogue staging: conflict-free float4 rows
     static_assert(128 * kSBuf + D <= kTmemCols && SMEM_TOTAL <= 227 * 1024, "budget");
+    static_assert(kBM * STAGE_LD * 4 <= kStages3 * K_TILE, "epilogue staging must fit in the queue-tile ring");
 };
 
-template <int D>
+// scale -> exp2 -> sum -> pack of one 32-column chunk against the reference max -m = ng2
+template <bool kPoly>
+__device__ __forceinline__ void softmax_chunk(const uint32_t (&v)[32], const float2 sc2, const float2 ng2, float2& la,
+                                              float2& lb, uint32_t (&pk)[16]) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        const float2 x01 = ffma2(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sc2, ng2);
+        const float2 x23 = ffma2(make_float2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), sc2, ng2);
+        const float2 p01 = make_float2(ex2(x01.x), ex2(x01.y));
+        const float2 p23 = make_float2(ex2(x23.x), kPoly ? ex2_poly(x23.y) : ex2(x23.y));
+        la = fadd2(la, p01);
+        lb = fadd2(lb, p23);
+        pk[j >> 1] = pack_bf16(p01.x, p01.y);
+        pk[(j >> 1) + 1] = pack_bf16(p23.x, p23.y);
+    }
+}
+__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32]) {
+    float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        m0 = fmaxf(fmaxf(m0, __uint_as_float(v[j])), __uint_as_float(v[j + 1]));
+        m1 = fmaxf(fmaxf(m1, __uint_as_float(v[j + 2])), __uint_as_float(v[j + 3]));
+    }
+    return fmaxf(m0, m1);
+}
+
+template <int D, bool kPoly>
 __global__ void __launch_bounds__(384, 1)
-nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+nce_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                int B, long long K_local, float scale_log2, int n_splits, float* __restrict__ part_m,
                float* __restrict__ part_l, float* __restrict__ part_mmax, float* __restrict__ part_O,
-               float* __restrict__ dbg_S, int ablate_arg) {
-    using C = Cfg2<D>;
-    // timing ablations (scripts/ablate_nce.py); compiled out of the product library
-    const int ablate = kAblateHooks ? ablate_arg : 0;
+               float* __restrict__ dbg_S, int hook_arg) {
+    using C = Cfg3<D>;
     constexpr int BN = C::BN;
     extern __shared__ uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mt = blockIdx.x, split = blockIdx.y;
-    // life-cycle trace (hooked build, bit 1024): clock64 stamps of the first and the last CTA of the grid
-    long long* life = nullptr;
-    if (kAblateHooks && (ablate & 1024) && dbg_S != nullptr) {
-        const bool first = mt == 0 && split == 0, last = mt == (int)gridDim.x - 1 && split == (int)gridDim.y - 1;
-        if (first || last) life = reinterpret_cast<long long*>(dbg_S + 2ll * B * 128) + 4096 + (last ? 32 : 0);
-    }
-#define LIFE(k) do { if (life) life[k] = clock64(); } while (0)
-    if (life && threadIdx.x == 0) {
-        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-        life[0] = clock64(); life[20] = (long long)gt;
-    }
     const int T_total = (int)((K_local + BN - 1) / BN);
     const int t0 = (int)((long long)T_total * split / n_splits);
     const int t1 = (int)((long long)T_total * (split + 1) / n_splits);
     const int nt = t1 - t0;
     const int row_base = mt * kBM;
+    // life-cycle trace (hooked build, bit 1024 of MOMA_TC_ABLATE): clock64 stamps of the first and the last CTA of the grid
+    long long* life = nullptr;
+    if (kAblateHooks && (hook_arg & 1024) && dbg_S != nullptr) {
+        const bool first = mt == 0 && split == 0, last = mt == (int)gridDim.x - 1 && split == (int)gridDim.y - 1;
+        if (first || last) life = reinterpret_cast<long long*>(dbg_S + 2ll * B * 128) + 4096 + (last ? 32 : 0);
+    }
+    float* dump_S = (kAblateHooks && (hook_arg & 1024)) ? nullptr : dbg_S;      // the score dump would distort the trace
+#define LIFE(k) do { if (kAblateHooks && life) life[k] = clock64(); } while (0)
+    if (kAblateHooks && life && threadIdx.x == 0) {
+        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        life[0] = clock64(); life[20] = (long long)gt;
+    }
 
     if (nt <= 0) {      // empty split: neutral partials
         pdl_wait();
@@ -596,23 +642,37 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     const uint32_t base = (raw + 1023u) & ~1023u;
     const uint32_t q_smem = base;
     const uint32_t kv_smem = base + C::Q_TILE;
-    Bars2* bars = reinterpret_cast<Bars2*>(smem_raw + (base - raw) + C::SMEM_DATA);
+    Bars3* bars = reinterpret_cast<Bars3*>(smem_raw + (base - raw) + C::SMEM_DATA);
     const uint32_t b_q_full = smem_u32(&bars->q_full);
     auto b_kv_full = [&](int s) { return smem_u32(&bars->kv_full[s]); };
-    auto b_kv_empty = [&](int s) { return smem_u32(&bars->kv_empty[s]); };
     auto b_s_full = [&](int b) { return smem_u32(&bars->s_full[b]); };
     auto b_p_full = [&](int b) { return smem_u32(&bars->p_full[b]); };
-    auto b_pv_done = [&](int b) { return smem_u32(&bars->pv_done[b]); };
+    auto b_pv_done = [&](int s) { return smem_u32(&bars->pv_done[s]); };
     const uint32_t b_o_final = smem_u32(&bars->o_final);
+    auto load_tile = [&](int i) {        // producer lane: queue tile t0 + i -> stage i % kStages3
+        const int s = i % kStages3;
+        mbar_expect_tx(b_kv_full(s), C::K_TILE);
+        for (int kb = 0; kb < C::KB; ++kb)
+            tma_load_2d(kv_smem + s * C::K_TILE + kb * C::K_BLOCK, &tmap_k, kb * 64, (t0 + i) * BN, b_kv_full(s));
+    };
+    const int n_early = nt < kStages3 ? nt : kStages3;      // tiles whose stage is free from the start
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_q);
         tma_prefetch_desc(&tmap_k);
         mbar_init(b_q_full, 1);
-        for (int s = 0; s < kStages2; ++s) { mbar_init(b_kv_full(s), 1); mbar_init(b_kv_empty(s), 1); }
-        for (int b = 0; b < kSBuf; ++b) { mbar_init(b_s_full(b), 1); mbar_init(b_p_full(b), 8); mbar_init(b_pv_done(b), 1); }
+        for (int s = 0; s < kStages3; ++s) { mbar_init(b_kv_full(s), 1); mbar_init(b_pv_done(s), 1); }
+        for (int b = 0; b < kSBuf; ++b) { mbar_init(b_s_full(b), 1); mbar_init(b_p_full(b), 8); }
         mbar_init(b_o_final, 1);
         fence_barrier_init();
+        // the loads do not need TMEM or the other warps: start them before the CTA-wide set-up barrier.  (The barriers
+        // they signal are initialised; nobody else touches a barrier before the __syncthreads below.)
+        pdl_wait();                       // Q is the preceding kernel's output
+        mbar_expect_tx(b_q_full, C::Q_TILE);
+        for (int kb = 0; kb < C::KB; ++kb)
+            tma_load_2d(q_smem + kb * C::Q_BLOCK, &tmap_q, kb * 64, row_base, b_q_full);
+        for (int i = 0; i < n_early; ++i) load_tile(i);
+        LIFE(3);
     }
     if (warp == 2) tmem_alloc(smem_u32(&bars->tmem_base), kTmemCols);
     tc_fence_before();
@@ -621,24 +681,16 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     const uint32_t tmem = bars->tmem_base;
     auto s_colf = [&](int b) { return tmem + (uint32_t)(b * 128); };
     if (threadIdx.x == 0) LIFE(1);
-    // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the tail of the preceding kernel
-    pdl_wait();
+    pdl_wait();                           // every thread that touches global memory is ordered after the preceding grid
     if (threadIdx.x == 0) LIFE(2);
 
     if (warp == 0) {
-        // ===================================================== TMA producer
+        // ===================================================== TMA producer (remaining tiles)
         if (lane == 0) {
-            mbar_expect_tx(b_q_full, C::Q_TILE);
-            for (int kb = 0; kb < C::KB; ++kb)
-                tma_load_2d(q_smem + kb * C::Q_BLOCK, &tmap_q, kb * 64, row_base, b_q_full);
-            for (int i = 0; i < nt; ++i) {
-                const int s = i % kStages2;
-                mbar_wait(b_kv_empty(s), ((i / kStages2) & 1) ^ 1, 301);
-                if (ablate & 64) { mbar_expect_tx(b_kv_full(s), 0); continue; }
-                mbar_expect_tx(b_kv_full(s), C::K_TILE);
-                for (int kb = 0; kb < C::KB; ++kb)
-                    tma_load_2d(kv_smem + s * C::K_TILE + kb * C::K_BLOCK, &tmap_k, kb * 64, (t0 + i) * BN, b_kv_full(s));
-                if (i == 0) LIFE(3);
+            for (int i = n_early; i < nt; ++i) {
+                // stage i % kStages3 is free once PV(i - kStages3) has completed
+                mbar_wait(b_pv_done(i % kStages3), ((i / kStages3) & 1) ^ 1, 301);
+                load_tile(i);
             }
         }
     } else if (warp == 1) {
@@ -651,8 +703,8 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             const uint64_t v_desc0 = make_desc(kv_smem, C::K_BLOCK, 1024);
             auto issue_s = [&](int b, int stage) {
                 const uint64_t db0 = k_desc0 + (uint64_t)((stage * C::K_TILE) >> 4);
-#pragma unroll 1
-                for (int ks = 0; ks < ((ablate & 8) ? 0 : D / 16); ++ks) {
+#pragma unroll
+                for (int ks = 0; ks < D / 16; ++ks) {
                     const uint32_t qoff = (uint32_t)((ks >> 2) * C::Q_BLOCK + (ks & 3) * 32) >> 4;
                     const uint32_t koff = (uint32_t)((ks >> 2) * C::K_BLOCK + (ks & 3) * 32) >> 4;
                     umma_ss(s_colf(b), q_desc0 + qoff, db0 + koff, idesc_s, ks > 0 ? 1u : 0u);
@@ -661,11 +713,11 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             };
             auto issue_pv = [&](int b, int stage, bool accumulate) {
                 const uint64_t db0 = v_desc0 + (uint64_t)((stage * C::K_TILE) >> 4);
-#pragma unroll 1
-                for (int ks = 0; ks < ((ablate & 4) ? 0 : BN / 16); ++ks)
-                    umma_ts(tmem + C::O_COL, s_colf(b) + ks * 8, db0 + (uint64_t)(ks * (2048 >> 4)), idesc_o,
-                            (accumulate || ks > 0) ? 1u : 0u);
-                umma_commit(b_pv_done(b));
+#pragma unroll
+                for (int ks = 0; ks < BN / 16; ++ks)      // P of keys [64h, 64h + 64) sits in score columns [64h, 64h + 32)
+                    umma_ts(tmem + C::O_COL, s_colf(b) + (uint32_t)((ks >> 2) * 64 + (ks & 3) * 8),
+                            db0 + (uint64_t)(ks * (2048 >> 4)), idesc_o, (accumulate || ks > 0) ? 1u : 0u);
+                umma_commit(b_pv_done(stage));
             };
             mbar_wait(b_q_full, 0, 302);
             mbar_wait(b_kv_full(0), 0, 303);
@@ -674,34 +726,21 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             issue_s(0, 0);
             LIFE(5);
             for (int j = 1; j < kSBuf && j < nt; ++j) { mbar_wait(b_kv_full(j), 0, 306); tc_fence_after(); issue_s(j, j); }
-            long long* tr = ((ablate & 256) && dbg_S != nullptr && mt == 0 && split == 0)
-                                ? reinterpret_cast<long long*>(dbg_S + 2ll * B * 128) : nullptr;
-            if (tr) tr[0] = clock64();
-            int* tri = ((ablate & 512) && tr) ? reinterpret_cast<int*>(tr) + 64 + 2048 : nullptr;
-#define IS_STAMP(k) if (tri && i >= 64 && i < 80) tri[(i - 64) * 8 + (k)] = (int)clock()
             for (int i = 0; i < nt; ++i) {
-                const int st = i % kStages2, b = i % kSBuf;
-                IS_STAMP(0);
+                const int st = i % kStages3, b = i % kSBuf;
                 mbar_wait(b_p_full(b), (i / kSBuf) & 1, 304);
                 tc_fence_after();
-                IS_STAMP(1);
                 issue_pv(b, st, i > 0);
-                umma_commit(b_kv_empty(st));
-                IS_STAMP(2);
                 if (i + kSBuf < nt) {
-                    const int sn = (i + kSBuf) % kStages2;
-                    mbar_wait(b_kv_full(sn), ((i + kSBuf) / kStages2) & 1, 305);
+                    const int sn = (i + kSBuf) % kStages3;
+                    mbar_wait(b_kv_full(sn), ((i + kSBuf) / kStages3) & 1, 305);
                     tc_fence_after();
-                    IS_STAMP(3);
                     issue_s(b, sn);
-                    IS_STAMP(4);
                 }
             }
-#undef IS_STAMP
             umma_commit(b_o_final);
             LIFE(8);
-            if (life) life[12] = nt;
-            if (tr) { tr[1] = clock64(); tr[2] = nt; }
+            if (kAblateHooks && life) life[12] = nt;
         }
     } else if (warp >= 4) {
         // ===================================================== softmax (two column halves)
@@ -716,126 +755,119 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const bool ragged_last = (K_local % BN) != 0;
         const float2 sc2 = make_float2(scale_log2, scale_log2);
 
-        int* trs = ((ablate & 512) && dbg_S != nullptr && mt == 0 && split == 0 && (warp == 4 || warp == 8) && lane == 0)
-                       ? reinterpret_cast<int*>(dbg_S + 2ll * B * 128) + 64 + (warp == 8 ? 1024 : 0) : nullptr;
-#define SM_STAMP(k) if (trs && i >= 64 && i < 80) trs[(i - 64) * 8 + (k)] = (int)clock()
         for (int i = 0; i < nt; ++i) {
             const int b = i % kSBuf;
-            SM_STAMP(0);
+            const uint32_t s_addr = s_colf(b) + lane_off + half * 64;      // this half's score columns; P goes over the first 32
             mbar_wait(b_s_full(b), (i / kSBuf) & 1, 401);
             tc_fence_after();
             if (i == 0 && warp == 4 && lane == 0) LIFE(6);
-            SM_STAMP(1);
-            uint32_t v[64];
-            if (ablate & 2) {
+            uint32_t v0[32], v1[32], pk0[16], pk1[16];
+            TMEM_LD32(s_addr, v0);
+            TMEM_WAIT_LD32(v0);
+            TMEM_LD32(s_addr + 32, v1);                       // in flight while chunk 0 is processed
+            if (dump_S != nullptr && i == 0 && split == 0 && row < B) {
 #pragma unroll
-                for (int j = 0; j < 64; ++j) { v[j] = 0x3c000000u + j; asm volatile("" : "+r"(v[j])); }
-            } else {
-                uint32_t* v0 = v; uint32_t* v1 = v + 32;
-                TMEM_LD32(s_colf(b) + lane_off + half * 64, v0);
-                TMEM_LD32(s_colf(b) + lane_off + half * 64 + 32, v1);
-                tmem_wait_ld();
+                for (int j = 0; j < 32; ++j) dump_S[(long long)row * BN + half * 64 + j] = __uint_as_float(v0[j]);
             }
-            if (dbg_S != nullptr && i == 0 && split == 0 && row < B) {
+            const bool ragged = ragged_last && (t0 + i) == T_total - 1;
+            const int valid = ragged ? (int)(K_local - (long long)(T_total - 1) * BN) - half * 64 : 64;
+            if (ragged) {
 #pragma unroll
-                for (int j = 0; j < 64; ++j) dbg_S[(long long)row * BN + half * 64 + j] = __uint_as_float(v[j]);
+                for (int j = 0; j < 32; ++j)
+                    if (j >= valid) v0[j] = __float_as_uint(-CUDART_INF_F);
             }
-            if (ragged_last && (t0 + i) == T_total - 1) {
-                const int valid = (int)(K_local - (long long)(T_total - 1) * BN) - half * 64;
+            float2 ng2 = make_float2(-m_ref, -m_ref);
+            float2 ta = make_float2(0.f, 0.f), tb = make_float2(0.f, 0.f);
+            float mxh = chunk_max(v0);
+            softmax_chunk<kPoly>(v0, sc2, ng2, ta, tb, pk0);          // speculative: against the CURRENT reference max
+            TMEM_WAIT_LD32(v1);
+            if (dump_S != nullptr && i == 0 && split == 0 && row < B) {
 #pragma unroll
-                for (int j = 0; j < 64; ++j)
-                    if (j >= valid) v[j] = __float_as_uint(-CUDART_INF_F);
+                for (int j = 0; j < 32; ++j) dump_S[(long long)row * BN + half * 64 + 32 + j] = __uint_as_float(v1[j]);
             }
-            SM_STAMP(2);
-            float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
+            if (ragged) {
 #pragma unroll
-            for (int j = 0; j < 64; j += 4) {
-                mx0 = fmaxf(fmaxf(mx0, __uint_as_float(v[j])), __uint_as_float(v[j + 1]));
-                mx1 = fmaxf(fmaxf(mx1, __uint_as_float(v[j + 2])), __uint_as_float(v[j + 3]));
+                for (int j = 0; j < 32; ++j)
+                    if (32 + j >= valid) v1[j] = __float_as_uint(-CUDART_INF_F);
             }
-            // exchange the half-row maxima with the thread holding the other 64 columns of this row
-            if (!(ablate & 32)) {
-                bars->xch[i & 1][half][rit] = fmaxf(mx0, mx1);
-                pair_barrier(1 + wq);
-            }
-            const float mx = (ablate & 32) ? 0.f : fmaxf(fmaxf(mx0, mx1), bars->xch[i & 1][half ^ 1][rit]) * scale_log2;
+            mxh = fmaxf(mxh, chunk_max(v1));
+            softmax_chunk<kPoly>(v1, sc2, ng2, ta, tb, pk1);
+            // the row max is only CHECKED: exchange the half-row maxima with the thread holding the other 64 columns
+            bars->xch[i & 1][half][rit] = mxh;
+            pair_barrier(1 + wq);
+            const float mx = fmaxf(mxh, bars->xch[i & 1][half ^ 1][rit]) * scale_log2;
             m_true = fmaxf(m_true, mx);
-            SM_STAMP(3);
-            const bool need = mx > m_ref + kLazyTau;                 // identical in both halves of the row
-            if (i > 0 && __any_sync(0xffffffffu, need)) {
-                mbar_wait(b_pv_done((i - 1) % kSBuf), ((i - 1) / kSBuf) & 1, 402);
-                tc_fence_after();
-                const float f = need ? ex2(m_ref - mx) : 1.0f;
+            const bool need = mx > m_ref + kLazyTau;                 // identical in both halves of the row; true on tile 0
+            if (__any_sync(0xffffffffu, need)) {
+                // rare after the first tile: move the reference, rescale O and l, redo this tile's P from the registers
+                if (i > 0) {
+                    mbar_wait(b_pv_done((i - 1) % kStages3), ((i - 1) / kStages3) & 1, 402);
+                    tc_fence_after();
+                    const float f = need ? ex2(m_ref - mx) : 1.0f;
 #pragma unroll 1
-                for (int c = 0; c < C::OH / 32; ++c) {
-                    uint32_t o[32];
-                    TMEM_LD32(o_addr + 32 * c, o);
-                    tmem_wait_ld();
+                    for (int c = 0; c < C::OH / 32; ++c) {
+                        uint32_t o[32];
+                        TMEM_LD32(o_addr + 32 * c, o);
+                        TMEM_WAIT_LD32(o);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * f);
-                    TMEM_ST32(o_addr + 32 * c, o);
-                }
-                tmem_wait_st();
-                l2a.x *= f; l2a.y *= f; l2b.x *= f; l2b.y *= f;
-            }
-            if (need) m_ref = mx;
-            const float2 ng2 = make_float2(-m_ref, -m_ref);
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t pk[16];
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float2 x01 = ffma2(make_float2(__uint_as_float(v[32 * c + j]), __uint_as_float(v[32 * c + j + 1])), sc2, ng2);
-                    const float2 x23 = ffma2(make_float2(__uint_as_float(v[32 * c + j + 2]), __uint_as_float(v[32 * c + j + 3])), sc2, ng2);
-                    float2 p01 = x01, p23 = x23;
-                    if (!(ablate & 1)) {
-                        p01 = make_float2(ex2(x01.x), ex2(x01.y));
-                        p23 = make_float2(ex2(x23.x), kPolyExp ? ex2_poly(x23.y) : ex2(x23.y));
+                        for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * f);
+                        TMEM_ST32(o_addr + 32 * c, o);
                     }
-                    l2a = fadd2(l2a, p01);
-                    l2b = fadd2(l2b, p23);
-                    pk[j >> 1] = pack_bf16(p01.x, p01.y);
-                    pk[(j >> 1) + 1] = pack_bf16(p23.x, p23.y);
+                    tmem_wait_st();
+                    l2a.x *= f; l2a.y *= f; l2b.x *= f; l2b.y *= f;
                 }
-                // P (bf16 pairs) aliases the S buffer: half h owns packed columns [32h, 32h + 32)
-                if (!(ablate & 16)) TMEM_ST16(s_colf(b) + lane_off + half * 32 + 16 * c, pk);
-                else if (pk[3] == 0x12345678u) bars->lsum[rit] = 0.f;      // keep the packs alive
+                if (need) m_ref = mx;
+                ng2 = make_float2(-m_ref, -m_ref);
+                ta = make_float2(0.f, 0.f); tb = make_float2(0.f, 0.f);
+                softmax_chunk<kPoly>(v0, sc2, ng2, ta, tb, pk0);
+                softmax_chunk<kPoly>(v1, sc2, ng2, ta, tb, pk1);
             }
-            SM_STAMP(4);
+            l2a = fadd2(l2a, ta);
+            l2b = fadd2(l2b, tb);
+            TMEM_ST16(s_addr, pk0);                           // P (bf16 pairs) over this half's own score columns
+            TMEM_ST16(s_addr + 16, pk1);
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
-            SM_STAMP(5);
             if (lane == 0) mbar_arrive(b_p_full(b));          // one arrival per warp: 8 instead of 256 smem atomics
             if (i == 0 && warp == 4 && lane == 0) LIFE(7);
-            SM_STAMP(6);
         }
-#undef SM_STAMP
 
         pdl_launch_dependents();     // the combine kernel may start launching; it still waits for this grid to finish
-        // epilogue: O (TMEM) -> part_O (each half writes its D/2 columns), stats by half 0
+        // epilogue: O (TMEM) -> shared-memory staging (padded rows) -> coalesced 128-bit stores; stats by half 0
         const float l_half = (l2a.x + l2a.y) + (l2b.x + l2b.y);
         if (half == 1) bars->lsum[rit] = l_half;
-        mbar_wait(b_o_final, 0, 403);
-        tc_fence_after();
+        mbar_wait(b_o_final, 0, 403);                         // every MMA (and with them every TMA load) has completed:
+        tc_fence_after();                                     // the queue-tile ring is free
         if (warp == 4 && lane == 0) LIFE(9);
-        const long long orow = (long long)split * B + row;
+        float* stage = reinterpret_cast<float*>(smem_raw + (base - raw) + C::Q_TILE);
 #pragma unroll 1
         for (int c = 0; c < C::OH / 32; ++c) {
             uint32_t o[32];
             TMEM_LD32(o_addr + 32 * c, o);
-            tmem_wait_ld();
-            if (row < B) {
-                float4* dst = reinterpret_cast<float4*>(part_O + orow * D + half * C::OH + 32 * c);
+            TMEM_WAIT_LD32(o);
+            float4* dst = reinterpret_cast<float4*>(stage + rit * C::STAGE_LD + half * C::OH + 32 * c);
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    dst[j] = make_float4(__uint_as_float(o[4 * j]), __uint_as_float(o[4 * j + 1]),
-                                         __uint_as_float(o[4 * j + 2]), __uint_as_float(o[4 * j + 3]));
+            for (int j = 0; j < 8; ++j)
+                dst[j] = make_float4(__uint_as_float(o[4 * j]), __uint_as_float(o[4 * j + 1]),
+                                     __uint_as_float(o[4 * j + 2]), __uint_as_float(o[4 * j + 3]));
+        }
+        group_barrier(5, 256);                                // all 8 softmax warps: staging complete (also publishes lsum)
+        {
+            constexpr int V4_PER_ROW = D / 4;
+            const int tid = threadIdx.x - 128;                // 0..255
+            float* out_base = part_O + ((long long)split * B + row_base) * D;
+#pragma unroll 4
+            for (int e = tid; e < kBM * V4_PER_ROW; e += 256) {
+                const int r = e / V4_PER_ROW, c4 = e - r * V4_PER_ROW;
+                if (row_base + r < B)
+                    st_stream(reinterpret_cast<float4*>(out_base + (long long)r * D) + c4,
+                              *reinterpret_cast<const float4*>(stage + r * C::STAGE_LD + 4 * c4));
             }
         }
-        pair_barrier(1 + wq);
         if (half == 0 && row < B) {
             constexpr float kLn2 = 0.6931471805599453f;
+            const long long orow = (long long)split * B + row;
             part_m[orow] = m_ref * kLn2;
             part_mmax[orow] = m_true * kLn2;
             part_l[orow] = l_half + bars->lsum[rit];
@@ -846,7 +878,7 @@ nce_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem, kTmemCols);
-    if (life && threadIdx.x == 0) {
+    if (kAblateHooks && life && threadIdx.x == 0) {
         unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         life[11] = clock64(); life[21] = (long long)gt;
     }
@@ -919,29 +951,40 @@ static void pick(int64_t B, int64_t D, int* nq, int* bn) {
     *bn = (D == 256) ? 64 : 128;
 }
 
-template <int D>
-static int launch2(const void* q, const void* queue, int64_t B, int64_t K_local, float inv_T, int n_splits,
+static bool use_poly_exp() {     // MOMA_B200_NCE_POLY=1: 25 % of the exp2 on the FMA pipe (A/B switch, read once)
+    static const bool on = [] { const char* e = getenv("MOMA_B200_NCE_POLY"); return e != nullptr && e[0] == '1'; }();
+    return on;
+}
+
+template <int D, bool kPoly>
+static int launch3(const void* q, const void* queue, int64_t B, int64_t K_local, float inv_T, int n_splits,
                    float* pm, float* pl, float* pmm, float* pO, float* dbg, cudaStream_t st) {
-    using C = Cfg2<D>;
+    using C = Cfg3<D>;
     CUtensorMap mq, mk;
     int rc = cached_map(&mq, q, B, D, kBM);
     if (rc != MOMA_OK) return rc;
     rc = cached_map(&mk, queue, K_local, D, C::BN);
     if (rc != MOMA_OK) return rc;
     {
-        const cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(nce_tc2_kernel<D>), C::SMEM_TOTAL);
+        const cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(nce_tc3_kernel<D, kPoly>), C::SMEM_TOTAL);
         if (e != cudaSuccess) take_launch_error();
-        MOMA_REQUIRE(e == cudaSuccess, MOMA_ERR_CUDA, "nce_tc2: smem attribute: %s", cudaGetErrorString(e));
+        MOMA_REQUIRE(e == cudaSuccess, MOMA_ERR_CUDA, "nce_tc3: smem attribute: %s", cudaGetErrorString(e));
     }
     const dim3 grid((unsigned)((B + kBM - 1) / kBM), (unsigned)n_splits);
     const float scale_log2 = inv_T * 1.4426950408889634f;
-    int ablate = 0;
-    if (kAblateHooks) { const char* e = getenv("MOMA_TC_ABLATE"); ablate = e ? atoi(e) : 0; }
-    launch_pdl(nce_tc2_kernel<D>, grid, dim3(C::THREADS), (size_t)C::SMEM_TOTAL, st, mq, mk, (int)B, (long long)K_local, scale_log2,
-               n_splits, pm, pl, pmm, pO, dbg, ablate);
-    MOMA_CUDA_LAUNCH_CHECK("nce_partial(bf16/tcgen05 v2)");
+    int hooks = 0;
+    if (kAblateHooks) { const char* e = getenv("MOMA_TC_ABLATE"); hooks = e ? atoi(e) : 0; }
+    launch_pdl(nce_tc3_kernel<D, kPoly>, grid, dim3(C::THREADS), (size_t)C::SMEM_TOTAL, st, mq, mk, (int)B, (long long)K_local,
+               scale_log2, n_splits, pm, pl, pmm, pO, dbg, hooks);
+    MOMA_CUDA_LAUNCH_CHECK("nce_partial(bf16/tcgen05 v3)");
     note_launches(1);
     return MOMA_OK;
+}
+template <int D>
+static int launch2(const void* q, const void* queue, int64_t B, int64_t K_local, float inv_T, int n_splits,
+                   float* pm, float* pl, float* pmm, float* pO, float* dbg, cudaStream_t st) {
+    return use_poly_exp() ? launch3<D, true>(q, queue, B, K_local, inv_T, n_splits, pm, pl, pmm, pO, dbg, st)
+                          : launch3<D, false>(q, queue, B, K_local, inv_T, n_splits, pm, pl, pmm, pO, dbg, st);
 }
 
 template <int D, int NQ, int BN>

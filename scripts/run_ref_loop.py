@@ -35,6 +35,10 @@ def main():
     ap.add_argument("--K", type=int, default=256)
     ap.add_argument("--D", type=int, default=128)
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--lr", type=float, default=0.002,
+                    help="SGD learning rate (the driver's default 0.05 makes a random-init ResNet-18 pair diverge within "
+                         "3 steps -- loss 7 -> 18 -> 58 -- which amplifies 1e-6 differences to 1e-3; parity is checked "
+                         "on a stable trajectory)")
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--port", type=int, default=29777)
     a = ap.parse_args()
@@ -78,7 +82,7 @@ def main():
     opt = argparse.Namespace(
         distill="moma", head="mlp", attn="self", mem="MoCo", feat_dim=a.D, nce_k=a.K, nce_t=0.15, alpha=0.999,
         gpu=0, rank=0, multiprocessing_distributed=True, batch_size=a.batch, print_freq=10 ** 9,
-        cls=1.0, div=1.0, beta=1.0, kd_T=4, learning_rate=0.05, momentum=0.9, weight_decay=5e-4,
+        cls=1.0, div=1.0, beta=1.0, kd_T=4, learning_rate=a.lr, momentum=0.9, weight_decay=5e-4,
         local_rank=0, node_rank=0, ngpus_per_node=1, world_size=1)
     trainer = ContrastTrainer(opt)
     trainer.local_group = dist.new_group(ranks=[0])
