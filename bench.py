@@ -112,9 +112,10 @@ class Ctx:
         self.args, self.rank, self.world, self.dist = args, rank, world, dist
         self.device = torch.device("cuda", local_rank)
         # L2 flush between steps: READ a 256 MiB buffer (leaves the 126 MB L2 full of clean foreign lines; a
-        # write-flush would leave it dirty and charge the write-back to the next kernel)
-        self.flush_buf = None if args.no_flush else torch.empty(64 << 20, dtype=torch.int32, device=self.device).zero_()
-        self.flush_out = torch.zeros(1, dtype=torch.int64, device=self.device)
+        # write-flush would leave it dirty and charge the write-back to the next kernel).  fp32 in, fp32 out: ONE reduce
+        # kernel (an int32 -> int64 sum first materialises a 512 MiB converted copy, i.e. it is a write-flush)
+        self.flush_buf = None if args.no_flush else torch.zeros(64 << 20, dtype=torch.float32, device=self.device)
+        self.flush_out = torch.zeros(1, dtype=torch.float32, device=self.device)
 
     def flush(self):
         if self.flush_buf is not None:

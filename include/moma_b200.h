@@ -270,6 +270,9 @@ double moma_debug_flops(int kind, int reset);
  * launched with the attribute starts while its predecessor drains and then waits, so profiler "durations" include
  * that wait: bench.py captures a second graph with PDL off to measure per-kernel shares. */
 int moma_debug_set_pdl(int enable);
+/* Launch-overhead probe: an empty kernel of `ctas` x `threads` with `smem_bytes` of dynamic shared memory, optionally
+ * allocating / releasing all TMEM columns (the launch shape of the InfoNCE kernel, without its work). */
+int moma_debug_probe_launch(int ctas, int threads, int smem_bytes, int use_tmem, int pdl, moma_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -48,6 +48,7 @@ SIGNATURES = {
     "moma_debug_launch_count": (ctypes.c_longlong, [c_int]),
     "moma_debug_flops": (ctypes.c_double, [c_int, c_int]),
     "moma_debug_set_pdl": (c_int, [c_int]),
+    "moma_debug_probe_launch": (c_int, [c_int, c_int, c_int, c_int, c_int, _vp]),
     "moma_attn_fwd_rows": (c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, c_int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "moma_attn_bwd_workspace_bytes": (c_size_t, [_i64, _i64, c_int]),
     "moma_attn_bwd": (c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, c_int,

@@ -596,7 +596,7 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&v)[32]) {
     return fmaxf(m0, m1);
 }
 
-template <int D, bool kPoly>
+template <int D, bool kPoly, bool kRagged>
 __global__ void __launch_bounds__(384, 1)
 nce_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                int B, long long K_local, float scale_log2, int n_splits, float* __restrict__ part_m,
@@ -752,7 +752,7 @@ nce_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         const uint32_t o_addr = tmem + lane_off + C::O_COL + half * C::OH;
         float m_ref = -CUDART_INF_F, m_true = -CUDART_INF_F;
         float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);     // running half-row sums
-        const bool ragged_last = (K_local % BN) != 0;
+        const bool ragged_last = kRagged && (K_local % BN) != 0;     // a separate instantiation: the common one has no masking code
         const float2 sc2 = make_float2(scale_log2, scale_log2);
 
         for (int i = 0; i < nt; ++i) {
@@ -771,7 +771,7 @@ nce_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             }
             const bool ragged = ragged_last && (t0 + i) == T_total - 1;
             const int valid = ragged ? (int)(K_local - (long long)(T_total - 1) * BN) - half * 64 : 64;
-            if (ragged) {
+            if (kRagged && ragged) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                     if (j >= valid) v0[j] = __float_as_uint(-CUDART_INF_F);
@@ -779,26 +779,27 @@ nce_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             float2 ng2 = make_float2(-m_ref, -m_ref);
             float2 ta = make_float2(0.f, 0.f), tb = make_float2(0.f, 0.f);
             float mxh = chunk_max(v0);
-            softmax_chunk<kPoly>(v0, sc2, ng2, ta, tb, pk0);          // speculative: against the CURRENT reference max
+            if (i > 0) softmax_chunk<kPoly>(v0, sc2, ng2, ta, tb, pk0);      // speculative: against the CURRENT reference max
+                                                                           // (tile 0 has none yet: its P is computed below)
             TMEM_WAIT_LD32(v1);
             if (dump_S != nullptr && i == 0 && split == 0 && row < B) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) dump_S[(long long)row * BN + half * 64 + 32 + j] = __uint_as_float(v1[j]);
             }
-            if (ragged) {
+            if (kRagged && ragged) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                     if (32 + j >= valid) v1[j] = __float_as_uint(-CUDART_INF_F);
             }
             mxh = fmaxf(mxh, chunk_max(v1));
-            softmax_chunk<kPoly>(v1, sc2, ng2, ta, tb, pk1);
+            if (i > 0) softmax_chunk<kPoly>(v1, sc2, ng2, ta, tb, pk1);
             // the row max is only CHECKED: exchange the half-row maxima with the thread holding the other 64 columns
             bars->xch[i & 1][half][rit] = mxh;
             pair_barrier(1 + wq);
             const float mx = fmaxf(mxh, bars->xch[i & 1][half ^ 1][rit]) * scale_log2;
             m_true = fmaxf(m_true, mx);
             const bool need = mx > m_ref + kLazyTau;                 // identical in both halves of the row; true on tile 0
-            if (__any_sync(0xffffffffu, need)) {
+            if (i == 0 || __any_sync(0xffffffffu, need)) {
                 // rare after the first tile: move the reference, rescale O and l, redo this tile's P from the registers
                 if (i > 0) {
                     mbar_wait(b_pv_done((i - 1) % kStages3), ((i - 1) / kStages3) & 1, 402);
@@ -956,7 +957,7 @@ static bool use_poly_exp() {     // MOMA_B200_NCE_POLY=1: 25 % of the exp2 on th
     return on;
 }
 
-template <int D, bool kPoly>
+template <int D, bool kPoly, bool kRagged>
 static int launch3(const void* q, const void* queue, int64_t B, int64_t K_local, float inv_T, int n_splits,
                    float* pm, float* pl, float* pmm, float* pO, float* dbg, cudaStream_t st) {
     using C = Cfg3<D>;
@@ -966,7 +967,7 @@ static int launch3(const void* q, const void* queue, int64_t B, int64_t K_local,
     rc = cached_map(&mk, queue, K_local, D, C::BN);
     if (rc != MOMA_OK) return rc;
     {
-        const cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(nce_tc3_kernel<D, kPoly>), C::SMEM_TOTAL);
+        const cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(nce_tc3_kernel<D, kPoly, kRagged>), C::SMEM_TOTAL);
         if (e != cudaSuccess) take_launch_error();
         MOMA_REQUIRE(e == cudaSuccess, MOMA_ERR_CUDA, "nce_tc3: smem attribute: %s", cudaGetErrorString(e));
     }
@@ -974,7 +975,7 @@ static int launch3(const void* q, const void* queue, int64_t B, int64_t K_local,
     const float scale_log2 = inv_T * 1.4426950408889634f;
     int hooks = 0;
     if (kAblateHooks) { const char* e = getenv("MOMA_TC_ABLATE"); hooks = e ? atoi(e) : 0; }
-    launch_pdl(nce_tc3_kernel<D, kPoly>, grid, dim3(C::THREADS), (size_t)C::SMEM_TOTAL, st, mq, mk, (int)B, (long long)K_local,
+    launch_pdl(nce_tc3_kernel<D, kPoly, kRagged>, grid, dim3(C::THREADS), (size_t)C::SMEM_TOTAL, st, mq, mk, (int)B, (long long)K_local,
                scale_log2, n_splits, pm, pl, pmm, pO, dbg, hooks);
     MOMA_CUDA_LAUNCH_CHECK("nce_partial(bf16/tcgen05 v3)");
     note_launches(1);
@@ -983,8 +984,12 @@ static int launch3(const void* q, const void* queue, int64_t B, int64_t K_local,
 template <int D>
 static int launch2(const void* q, const void* queue, int64_t B, int64_t K_local, float inv_T, int n_splits,
                    float* pm, float* pl, float* pmm, float* pO, float* dbg, cudaStream_t st) {
-    return use_poly_exp() ? launch3<D, true>(q, queue, B, K_local, inv_T, n_splits, pm, pl, pmm, pO, dbg, st)
-                          : launch3<D, false>(q, queue, B, K_local, inv_T, n_splits, pm, pl, pmm, pO, dbg, st);
+    const bool ragged = (K_local % 128) != 0;
+    if (use_poly_exp())
+        return ragged ? launch3<D, true, true>(q, queue, B, K_local, inv_T, n_splits, pm, pl, pmm, pO, dbg, st)
+                      : launch3<D, true, false>(q, queue, B, K_local, inv_T, n_splits, pm, pl, pmm, pO, dbg, st);
+    return ragged ? launch3<D, false, true>(q, queue, B, K_local, inv_T, n_splits, pm, pl, pmm, pO, dbg, st)
+                  : launch3<D, false, false>(q, queue, B, K_local, inv_T, n_splits, pm, pl, pmm, pO, dbg, st);
 }
 
 template <int D, int NQ, int BN>
@@ -1073,4 +1078,33 @@ extern "C" __attribute__((visibility("default"))) int moma_debug_tc_error(void) 
     int v = 0;
     if (cudaMemcpyFromSymbol(&v, tc::g_tc_error, sizeof(int)) != cudaSuccess) { cudaGetLastError(); return -1; }
     return v;
+}
+
+// Launch-overhead probe (bench / profiling only): an otherwise empty kernel with a given dynamic shared-memory size,
+// optionally allocating and releasing all 512 TMEM columns -- what a launch of the InfoNCE kernel's shape costs
+// before it does any work.
+namespace moma { namespace tc {
+__global__ void __launch_bounds__(384, 1) probe_kernel(int use_tmem, int* sink) {
+    extern __shared__ uint8_t probe_smem[];
+    __shared__ uint32_t tmem_slot;
+    if (use_tmem) {
+        if ((threadIdx.x >> 5) == 2) tmem_alloc(smem_u32(&tmem_slot), kTmemCols);
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if ((threadIdx.x >> 5) == 2) tmem_dealloc(tmem_slot, kTmemCols);
+    }
+    if (sink != nullptr && threadIdx.x == 0 && probe_smem[0] == 123) sink[0] = 1;
+}
+} }
+extern "C" __attribute__((visibility("default"))) int moma_debug_probe_launch(int ctas, int threads, int smem_bytes, int use_tmem,
+                                                                              int pdl, moma_stream_t stream) {
+    MOMA_REQUIRE(ctas > 0 && threads > 0 && threads <= 384 && smem_bytes >= 0 && smem_bytes <= 227 * 1024, MOMA_ERR_INVALID,
+                 "probe_launch: bad arguments");
+    cudaError_t e = cudaFuncSetAttribute(tc::probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64);
+    MOMA_REQUIRE(e == cudaSuccess, MOMA_ERR_CUDA, "probe_launch: %s", cudaGetErrorString(e));
+    if (pdl) launch_pdl(tc::probe_kernel, dim3(ctas), dim3(threads), (size_t)smem_bytes, as_stream(stream), use_tmem, (int*)nullptr);
+    else tc::probe_kernel<<<ctas, threads, smem_bytes, as_stream(stream)>>>(use_tmem, nullptr);
+    MOMA_CUDA_LAUNCH_CHECK("probe_launch");
+    return MOMA_OK;
 }

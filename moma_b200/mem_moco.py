@@ -281,9 +281,13 @@ class MoCoAtt(BaseMoCo):
     def forward(self, q, k, all_k=None, attn=None, criterion_kd=None):
         bsz = q.size(0)
         k = k.detach()
-        # the attended queue is a new tensor every step (no clone needed for the untouched case:
-        # the loss pass below is stream-ordered before the enqueue)
+        # The reference clones the queue (:119).  Where the queue only feeds the fused loss pass, no copy is needed
+        # (stream order: the pass reads it before the enqueue overwrites it).  Where it is an INPUT OF AN ATTENTION
+        # MODULE under autograd ('all', 'dual' and the default mode), that module saves its input for the backward of
+        # its weights, and the enqueue below would overwrite the saved rows behind autograd's back: copy it.
         queue = self.memory.detach()
+        if torch.is_grad_enabled() and attn not in ('qk', 'dual2', 'self_qk', 'self_qkv2'):
+            queue = queue.clone()
         if attn == 'all':
             out = criterion_kd.atts(torch.cat([q, k, queue], dim=0))
             q, k, queue = out[:bsz], out[bsz:2 * bsz], out[2 * bsz:]

@@ -13,7 +13,7 @@ cases = [(512, 65536), (256, 16384)] if len(sys.argv) < 3 else [(int(sys.argv[1]
 names = ["entry", "setup done (bar init, TMEM alloc, sync)", "after griddepcontrol.wait", "producer: first queue tile issued",
          "issuer: Q + first tile landed", "issuer: first S issued", "softmax: first S complete", "softmax: first P handed over",
          "issuer: last PV issued (o_final commit)", "softmax: O final", "softmax: partials stored", "CTA exit"]
-flush = torch.empty(64 << 20, dtype=torch.int32, device="cuda").zero_()
+flush = torch.zeros(64 << 20, dtype=torch.float32, device="cuda")
 for B, K in cases:
     splits = lib.moma_nce_num_splits(B, D, K, BF16)
     q = torch.randn(B, D, device="cuda").to(torch.bfloat16)

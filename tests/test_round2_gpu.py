@@ -129,7 +129,10 @@ def test_mocoatt_modes_golden(fp32, golden, opt_attn, mode):
         has = bool(g[tag + "hasgrad_" + n_])
         assert (p_.grad is not None) == has, (mode, n_)
         if has:
-            assert rel(npy(p_.grad), g[tag + "grad_" + n_]) < 5 * TOL, (mode, n_)
+            # both sides are fp32 runs (the golden is the reference on CPU): 1e-4, plus an absolute floor for
+            # gradients that are mathematically zero (the key part of qkv.bias: softmax is shift-invariant)
+            want = g[tag + "grad_" + n_]
+            assert np.linalg.norm(npy(p_.grad) - want) < 1e-4 * np.linalg.norm(want) + 1e-6, (mode, n_)
     assert m.index == int(g[tag + "index"])
     ids = O.enqueue_ids(6, 20, 24)
     untouched = np.setdiff1d(np.arange(24), ids)
@@ -161,7 +164,8 @@ def test_mocoatt_attended_queue_bf16_no_stale_shadow(bf16, golden):
             att("atts_queue", mem)
         loss_o, _, _, _ = O.nce_loss_and_grad(r(q2), r(k2), r(queue2), T)
         assert abs(loss.item() - loss_o) < 1e-3 * abs(loss_o), step
-        assert len(m._shadows) == 0                    # nothing cached for the transient queue
+        assert set(m._shadows) <= {"memory"}           # only the registered buffer's shadow is cached, none for the
+                                                       # transient attended queue
 
 
 # ------------------------------------------------------------------ heads other than 'mlp'
@@ -182,7 +186,8 @@ def test_heads_golden(fp32, golden, head):
     assert rel(npy(y), g[f"{head}_y"]) < 2 * TOL
     assert rel(npy(x.grad), g[f"{head}_dx"]) < 5 * TOL
     for n_, p_ in emb.named_parameters():
-        assert rel(npy(p_.grad), g[f"{head}_grad_{n_}"]) < 5 * TOL, n_
+        want = g[f"{head}_grad_{n_}"]                    # absolute floor: the bias in front of a train-mode BatchNorm
+        assert np.linalg.norm(npy(p_.grad) - want) < 5 * TOL * np.linalg.norm(want) + 1e-6, n_     # has zero gradient
     for n_, p_ in emb.state_dict().items():
         assert rel(npy(p_), g[f"{head}_sd1_{n_}"]) < 2 * TOL, n_
 
