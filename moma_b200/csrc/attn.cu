@@ -13,6 +13,13 @@
 
 namespace moma {
 
+// attn_tc.cu: the attention core on the tensor cores (3xTF32 mma.sync) for head_dim 8 / 16 / 32
+bool attn_tc_supported(int hd);
+void attn_tc_fwd(const float* qkv, int N, int C, int H, float scale, float* o, float* lse, cudaStream_t st, int q_start,
+                 int q_stride, int NQ);
+void attn_tc_bwd(const float* qkv, const float* dO, const float* lse, const float* delta, int N, int C, int H, float scale,
+                 float* dqkv, cudaStream_t st, cudaStream_t st2);
+
 // ------------------------------------------------------------------ generic SGEMM
 // C[m, n] = sum_k A(m,k) * B(n,k) (+ bias[n]);  A(m,k) = A[m*a_rs + k*a_cs], same for B.
 // The GEMMs of this path are tiny (M, N, K in the hundreds) and latency-bound, so the kernel is
@@ -640,7 +647,8 @@ extern "C" __attribute__((visibility("default"))) int moma_attn_fwd(const float*
     const int n = (int)N, c = (int)C, hd = c / H;
     const float scale = 1.0f / sqrtf((float)hd);
     sgemm(x, C, 1, w_qkv, C, 1, b_qkv, qkv, 3 * C, n, 3 * c, c, st);
-    switch (hd) {
+    if (attn_tc_supported(hd)) attn_tc_fwd(qkv, n, c, H, scale, o, lse, st, 0, 1, n);
+    else switch (hd) {
         case 8: launch_fwd<8>(qkv, n, c, H, scale, o, lse, st); break;
         case 16: launch_fwd<16>(qkv, n, c, H, scale, o, lse, st); break;
         case 32: launch_fwd<32>(qkv, n, c, H, scale, o, lse, st); break;
@@ -680,7 +688,8 @@ extern "C" __attribute__((visibility("default"))) int moma_attn_fwd_rows(
     const float scale = 1.0f / sqrtf((float)hd);
     // x == NULL: qkv already holds the projections of all N tokens (e.g. all-gathered from the ranks that own them)
     if (x != nullptr) sgemm(x, C, 1, w_qkv, C, 1, b_qkv, qkv, 3 * C, n, 3 * c, c, st);
-    switch (hd) {
+    if (attn_tc_supported(hd)) attn_tc_fwd(qkv, n, c, H, scale, o, lse, st, (int)q_start, (int)q_stride, nq);
+    else switch (hd) {
         case 8: launch_fwd<8>(qkv, n, c, H, scale, o, lse, st, (int)q_start, (int)q_stride, nq); break;
         case 16: launch_fwd<16>(qkv, n, c, H, scale, o, lse, st, (int)q_start, (int)q_stride, nq); break;
         case 32: launch_fwd<32>(qkv, n, c, H, scale, o, lse, st, (int)q_start, (int)q_stride, nq); break;
@@ -724,8 +733,9 @@ extern "C" __attribute__((visibility("default"))) int moma_attn_bwd(const float*
     BwdStreams& bs = bwd_streams();
     cudaStream_t s1 = bs.ok ? bs.s1 : st, s2 = bs.ok ? bs.s2 : st;
     if (bs.ok) { cudaEventRecord(bs.fork, st); cudaStreamWaitEvent(s1, bs.fork, 0); }
+    const bool tc = attn_tc_supported(hd);
     bool split = false;
-    switch (hd) {
+    if (!tc) switch (hd) {
         case 8: split = dkv_wants_split<8>(n, H); break;
         case 16: split = dkv_wants_split<16>(n, H); break;
         case 32: split = dkv_wants_split<32>(n, H); break;
@@ -742,7 +752,8 @@ extern "C" __attribute__((visibility("default"))) int moma_attn_bwd(const float*
     sgemm(grad_y, C, 1, w_proj, 1, C, nullptr, dO, C, n, c, c, st);
     launch_pdl(attn_delta_kernel, dim3((n * H + 3) / 4), dim3(128), 0, st, dO, o, n, c, H, delta);
     if (bs.ok) { cudaEventRecord(bs.d_o, st); cudaStreamWaitEvent(s2, bs.d_o, 0); }
-    switch (hd) {
+    if (tc) attn_tc_bwd(qkv, dO, lse, delta, n, c, H, scale, dqkv, st, s2);
+    else switch (hd) {
         case 8: launch_bwd<8>(qkv, dO, lse, delta, n, c, H, scale, dqkv, st, s2, split); break;
         case 16: launch_bwd<16>(qkv, dO, lse, delta, n, c, H, scale, dqkv, st, s2, split); break;
         case 32: launch_bwd<32>(qkv, dO, lse, delta, n, c, H, scale, dqkv, st, s2, split); break;

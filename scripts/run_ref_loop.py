@@ -124,7 +124,7 @@ def main():
     losses, states = [], []
 
     def csum(ts):
-        return float(sum(t.detach().double().abs().sum() for t in ts).item())
+        return float(sum(float(t.detach().double().abs().sum().item()) for t in ts))
 
     for it, batch in enumerate(batches):                               # one-batch "epochs": the loop returns that step's loss
         _, loss_avg = train_distill_moma(it + 1, [batch], module_list, criterion_list, trainer, contrast, optimizer, opt)
@@ -143,8 +143,8 @@ def main():
     torch.cuda.synchronize()
     mem = contrast.memory if hasattr(contrast, "memory") else None
     trained = [p for p in trainable_list.parameters()]
-    out = {"arm": a.arm, "param_abs_sum": float(sum(p.detach().double().abs().sum() for p in trained).item()),
-           "grad_abs_sum": float(sum(p.grad.detach().double().abs().sum() for p in trained if p.grad is not None).item()), "origin": origin, "precision": a.precision if a.arm == "ours" else "fp32 (stock)",
+    out = {"arm": a.arm, "param_abs_sum": csum(trained),
+           "grad_abs_sum": csum(p.grad for p in trained if p.grad is not None), "origin": origin, "precision": a.precision if a.arm == "ours" else "fp32 (stock)",
            "losses": losses, "states": states, "index": int(contrast.index), "lr": a.lr,
            "queue_sum": float(mem.double().sum().item()), "queue_abs_sum": float(mem.double().abs().sum().item()),
            "config": {"batch": a.batch, "size": a.size, "K": a.K, "D": a.D, "s_dim": opt.s_dim, "t_dim": opt.t_dim}}
