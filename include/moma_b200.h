@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MOMA_ABI_VERSION 2
+#define MOMA_ABI_VERSION 3
 
 typedef void *moma_stream_t; /* cudaStream_t / CUstream */
 
@@ -162,6 +162,27 @@ int moma_nce_combine_packed(const float *packed, int n_parts, const float *q_f32
                             const float *kpos_f32, int64_t B, int64_t D, float inv_T, int round_bf16,
                             float dq_scale, float *loss_rows, float *dq_unit, int32_t *pos_is_max,
                             float *max_logit, float *loss_mean, float *acc_pct, moma_stream_t stream);
+/* One launch for the whole InfoNCE pass (bf16 operands, D = 64 or 128): the tcgen05 partial kernel, and in its tail the
+ * combine -- every CTA waits (bounded) for the other K-splits of its query tile, then combines a slice of the tile's rows;
+ * the last CTA of the grid reduces the loss rows to loss_mean / acc_pct.  Same outputs as moma_nce_partial +
+ * moma_nce_combine (replaces MoMA/mem_moco.py:29-49,89 + learning/contrast_trainer.py:189-205 and their backward).
+ *   workspace : moma_nce_fused_workspace_bytes() bytes, 16-byte aligned (the split partials; L2-resident between the phases)
+ *   counters  : >= 256 uint32, ZERO before the first use; the kernel leaves them zero.  Not shared between launches
+ *               that may run concurrently.
+ * moma_nce_fused_supported: shape check (the grid must fit one CTA per SM: B / 128 * splits <= SM count).
+ * moma_nce_fused_packed: same pass, but the tail emits one merged packed record per query row, [B, D + 4] =
+ *   (O | m | l | mmax | pad) -- the unit the K-sharded queue exchanges between ranks (then moma_nce_combine_packed). */
+int moma_nce_fused_supported(int64_t B, int64_t D, int64_t K_local);
+size_t moma_nce_fused_workspace_bytes(int64_t B, int64_t D, int64_t K_local);
+int moma_nce_fused(const void *q_bf16, const void *queue_bf16, const float *q_f32, const float *kpos_f32,
+                   int64_t B, int64_t D, int64_t K_local, float inv_T, int round_bf16, float dq_scale,
+                   void *workspace, size_t workspace_bytes, uint32_t *counters, float *loss_rows,
+                   float *dq_unit, int32_t *pos_is_max, float *max_logit, float *loss_mean, float *acc_pct,
+                   moma_stream_t stream);
+int moma_nce_fused_packed(const void *q_bf16, const void *queue_bf16, int64_t B, int64_t D, int64_t K_local,
+                          float inv_T, void *workspace, size_t workspace_bytes, uint32_t *counters,
+                          float *packed, moma_stream_t stream);
+
 /* Escape hatch / tests: materialise logits[B, K+1] = cat(q.k, q queue^T) / T
  * exactly as mem_moco.py:29-49 lays them out (row stride K+1). */
 int moma_nce_logits(const void *q, const void *kpos, const void *queue, int64_t B, int64_t D,

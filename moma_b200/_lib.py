@@ -12,7 +12,7 @@ from ctypes import (POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_
 from . import _build
 
 F32, BF16 = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _vp = c_void_p
 _i64 = c_int64
@@ -40,6 +40,11 @@ SIGNATURES = {
     "moma_nce_merge_packed": (c_int, [_vp, _vp, _vp, _vp, c_int, _i64, _i64, _vp, _vp]),
     "moma_nce_combine_packed": (c_int, [_vp, c_int, _vp, _vp, _i64, _i64, c_float, c_int, c_float,
                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "moma_nce_fused_supported": (c_int, [_i64, _i64, _i64]),
+    "moma_nce_fused_workspace_bytes": (c_size_t, [_i64, _i64, _i64]),
+    "moma_nce_fused": (c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, c_float, c_int, c_float, _vp, c_size_t, _vp,
+                               _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "moma_nce_fused_packed": (c_int, [_vp, _vp, _i64, _i64, _i64, c_float, _vp, c_size_t, _vp, _vp, _vp]),
     "moma_nce_logits": (c_int, [_vp, _vp, _vp, _i64, _i64, _i64, c_float, c_int, _vp, _vp]),
     "moma_nce_logits_qk": (c_int, [_vp, _vp, _i64, _i64, c_float, _vp, _vp]),
     "moma_attn_fwd": (c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

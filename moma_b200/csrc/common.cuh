@@ -51,6 +51,26 @@ int gemm_nt(const float* A, const float* a_mask, int64_t a_rs, int64_t a_cs, con
 void colsum_masked(const float* X, const float* mask, int rows, int cols, float* out, cudaStream_t st);
 bool use_simt_gemm();        // MOMA_B200_GEMM=simt: IEEE-FP32 CUDA-core GEMMs instead (A/B switch, read once)
 
+// Arguments of the in-kernel combine of the tcgen05 InfoNCE kernel (nce_tc.cu; filled by the entry points in nce_simt.cu)
+namespace tc {
+enum : int { kFuseNone = 0, kFuseFinal = 1, kFusePacked = 2 };
+struct NceFuse {
+    int mode;
+    const float* q_f32;          // [B, D] fp32 queries / positive keys (final mode)
+    const float* kpos_f32;
+    float inv_T, dq_scale;
+    int round_bf16;
+    float* loss_rows;            // [B]
+    float* dq;                   // [B, D]
+    int32_t* pos_is_max;         // [B]
+    float* max_logit;            // [B] (nullable)
+    float* loss_mean;            // [1] (nullable, with acc_pct)
+    float* acc_pct;              // [1]
+    float* packed;               // [B, D + 4] (packed mode)
+    unsigned int* counters;      // [query tiles + 1], zero between launches
+};
+}  // namespace tc
+
 // Programmatic dependent launch: a kernel launched through launch_pdl() may start while its predecessor in the stream is
 // still draining; it must call pdl_wait() before touching anything a predecessor wrote (or reads -- WAR) and may call
 // pdl_launch_dependents() as soon as its successor is allowed to start launching.  Both are no-ops for kernels launched

@@ -22,6 +22,10 @@ int nce_tc_partial(const void* q, const void* queue, int64_t B, int64_t D, int64
                    float* part_O, cudaStream_t stream);        // nce_tc.cu
 int nce_tc_num_splits(int64_t B, int64_t D, int64_t K_local);  // nce_tc.cu
 bool nce_tc_supported(int64_t B, int64_t D, int64_t K_local);  // nce_tc.cu
+bool nce_fused_supported(int64_t B, int64_t D, int64_t K_local);
+size_t nce_fused_workspace_floats(int64_t B, int64_t D, int64_t K_local);
+int nce_fused_launch(const void* q_bf16, const void* queue_bf16, int64_t B, int64_t D, int64_t K_local, float inv_T,
+                     float* workspace, const tc::NceFuse& fuse, cudaStream_t stream);
 
 // ------------------------------------------------------------------ fp32 partial
 // CTA = 256 threads = 8 warps; BM = 32 query rows (4 per warp), BN queue rows per
@@ -533,6 +537,47 @@ extern "C" __attribute__((visibility("default"))) int moma_nce_combine_packed(
         note_launches(1);
     }
     return MOMA_OK;
+}
+
+// ---- one launch for the whole pass: tcgen05 partial kernel + in-kernel combine (D = 64 / 128, bf16 operands)
+extern "C" __attribute__((visibility("default"))) int moma_nce_fused_supported(int64_t B, int64_t D, int64_t K_local) {
+    return nce_fused_supported(B, D, K_local) ? 1 : 0;
+}
+extern "C" __attribute__((visibility("default"))) size_t moma_nce_fused_workspace_bytes(int64_t B, int64_t D, int64_t K_local) {
+    if (!nce_fused_supported(B, D, K_local)) return 0;
+    return nce_fused_workspace_floats(B, D, K_local) * sizeof(float);
+}
+extern "C" __attribute__((visibility("default"))) int moma_nce_fused(
+    const void* q_bf16, const void* queue_bf16, const float* q_f32, const float* kpos_f32, int64_t B, int64_t D,
+    int64_t K_local, float inv_T, int round_bf16, float dq_scale, void* workspace, size_t workspace_bytes,
+    uint32_t* counters, float* loss_rows, float* dq_unit, int32_t* pos_is_max, float* max_logit, float* loss_mean,
+    float* acc_pct, moma_stream_t stream) {
+    MOMA_REQUIRE(nce_fused_supported(B, D, K_local), MOMA_ERR_UNSUPPORTED, "nce_fused: unsupported shape B=%lld D=%lld K=%lld",
+                 (long long)B, (long long)D, (long long)K_local);
+    MOMA_REQUIRE(q_bf16 && queue_bf16 && q_f32 && kpos_f32 && workspace && counters && loss_rows && dq_unit && pos_is_max,
+                 MOMA_ERR_INVALID, "nce_fused: null pointer");
+    MOMA_REQUIRE((loss_mean == nullptr) == (acc_pct == nullptr), MOMA_ERR_INVALID, "nce_fused: loss_mean and acc_pct go together");
+    MOMA_REQUIRE(workspace_bytes >= moma_nce_fused_workspace_bytes(B, D, K_local) && aligned16(workspace), MOMA_ERR_WORKSPACE,
+                 "nce_fused: workspace too small or unaligned");
+    MOMA_REQUIRE(aligned16(q_f32) && aligned16(kpos_f32) && aligned16(dq_unit), MOMA_ERR_ALIGN, "nce_fused: unaligned pointer");
+    MOMA_REQUIRE(inv_T > 0.f, MOMA_ERR_INVALID, "nce_fused: temperature must be positive");
+    tc::NceFuse f{};
+    f.mode = 1; f.q_f32 = q_f32; f.kpos_f32 = kpos_f32; f.inv_T = inv_T; f.dq_scale = dq_scale; f.round_bf16 = round_bf16;
+    f.loss_rows = loss_rows; f.dq = dq_unit; f.pos_is_max = pos_is_max; f.max_logit = max_logit; f.loss_mean = loss_mean;
+    f.acc_pct = acc_pct; f.packed = nullptr; f.counters = counters;
+    return nce_fused_launch(q_bf16, queue_bf16, B, D, K_local, inv_T, static_cast<float*>(workspace), f, as_stream(stream));
+}
+extern "C" __attribute__((visibility("default"))) int moma_nce_fused_packed(
+    const void* q_bf16, const void* queue_bf16, int64_t B, int64_t D, int64_t K_local, float inv_T, void* workspace,
+    size_t workspace_bytes, uint32_t* counters, float* packed, moma_stream_t stream) {
+    MOMA_REQUIRE(nce_fused_supported(B, D, K_local), MOMA_ERR_UNSUPPORTED, "nce_fused_packed: unsupported shape");
+    MOMA_REQUIRE(q_bf16 && queue_bf16 && workspace && counters && packed, MOMA_ERR_INVALID, "nce_fused_packed: null pointer");
+    MOMA_REQUIRE(workspace_bytes >= moma_nce_fused_workspace_bytes(B, D, K_local) && aligned16(workspace) && aligned16(packed),
+                 MOMA_ERR_WORKSPACE, "nce_fused_packed: workspace too small or unaligned");
+    MOMA_REQUIRE(inv_T > 0.f, MOMA_ERR_INVALID, "nce_fused_packed: temperature must be positive");
+    tc::NceFuse f{};
+    f.mode = 2; f.inv_T = inv_T; f.dq_scale = 1.f; f.packed = packed; f.counters = counters;
+    return nce_fused_launch(q_bf16, queue_bf16, B, D, K_local, inv_T, static_cast<float*>(workspace), f, as_stream(stream));
 }
 
 extern "C" __attribute__((visibility("default"))) int moma_nce_logits(const void* q, const void* kpos, const void* queue, int64_t B,

@@ -596,12 +596,114 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&v)[32]) {
     return fmaxf(m0, m1);
 }
 
+// ---- in-kernel combine (one launch for the whole InfoNCE pass) ---------------------------------------------------------
+// After a CTA has written its split partial it takes a ticket on its query tile; when all n_splits CTAs of the tile have
+// arrived, EVERY one of them combines a slice of the tile's 128 rows (rows split, split + n_splits, ...): merge of the
+// split partials in split order (deterministic), then -- mode kFuseFinal -- the positive column, loss row, d loss / d q and
+// the top-1 flag, or -- mode kFusePacked -- one packed record per row for the cross-rank exchange.  The last CTA of the
+// GRID (second ticket) reduces the loss rows to the mean / accuracy and zeroes the counters for the next launch.
+// Waiting on other CTAs is safe here: the grid never exceeds one CTA per SM (nce_tc_num_splits), so all of its CTAs are
+// co-resident as soon as whatever else runs on the GPU has drained; the wait is bounded and traps instead of hanging.
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float bf16_rne(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// One warp combines one row.  Lane `lane` owns columns [4 * lane, 4 * lane + 4) (lanes >= D / 4 idle along the columns).
+template <int D>
+__device__ __forceinline__ void fuse_combine_row(const NceFuse& f, int row, int B, int n_splits, const float* part_m,
+                                                 const float* part_l, const float* part_mmax, const float* part_O, int lane) {
+    constexpr int kMaxPer = 5;                         // n_splits <= 160
+    float ms[kMaxPer], w[kMaxPer];
+    float mref = -CUDART_INF_F, mtrue = -CUDART_INF_F;
+#pragma unroll
+    for (int i = 0; i < kMaxPer; ++i) {
+        const int sidx = lane + 32 * i;
+        ms[i] = sidx < n_splits ? __ldcg(part_m + (long long)sidx * B + row) : -CUDART_INF_F;
+        const float mt_ = sidx < n_splits ? __ldcg(part_mmax + (long long)sidx * B + row) : -CUDART_INF_F;
+        mref = fmaxf(mref, ms[i]); mtrue = fmaxf(mtrue, mt_);
+    }
+    mref = warp_max(mref); mtrue = warp_max(mtrue);
+    const bool fin = f.mode == kFuseFinal;
+    const bool col_ok = 4 * lane < D;
+    float4 kv = make_float4(0.f, 0.f, 0.f, 0.f);
+    float pos = 0.f;
+    if (fin) {
+        float dot = 0.f;
+        if (col_ok) {
+            float4 qv = *reinterpret_cast<const float4*>(f.q_f32 + (long long)row * D + 4 * lane);
+            kv = *reinterpret_cast<const float4*>(f.kpos_f32 + (long long)row * D + 4 * lane);
+            if (f.round_bf16) {
+                qv = make_float4(bf16_rne(qv.x), bf16_rne(qv.y), bf16_rne(qv.z), bf16_rne(qv.w));
+                kv = make_float4(bf16_rne(kv.x), bf16_rne(kv.y), bf16_rne(kv.z), bf16_rne(kv.w));
+            }
+            dot = qv.x * kv.x + qv.y * kv.y + qv.z * kv.z + qv.w * kv.w;
+        }
+        pos = warp_sum(dot) * f.inv_T;
+    }
+    const float mstar = fin ? fmaxf(mref, pos) : mref;
+    const float wpos = fin ? expf(pos - mstar) : 0.f;
+    float lsum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxPer; ++i) {
+        const int sidx = lane + 32 * i;
+        w[i] = (sidx < n_splits && ms[i] > -CUDART_INF_F) ? expf(ms[i] - mstar) : 0.f;
+        if (sidx < n_splits) lsum += w[i] * __ldcg(part_l + (long long)sidx * B + row);
+    }
+    const float l_tot = warp_sum(lsum) + wpos;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* Op = part_O + (long long)row * D + 4 * lane;
+    for (int s0 = 0; s0 < n_splits; s0 += 32) {
+        const float wl = w[0];                         // rotated below: w[0] always holds the weights of splits s0 .. s0 + 31
+        const int cnt = min(32, n_splits - s0);
+        for (int j = 0; j < cnt; j += 4) {             // 4 independent 128-bit loads in flight per lane
+            float4 v[4];
+            float ww[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int sidx = s0 + j + u;
+                ww[u] = __shfl_sync(0xffffffffu, wl, (j + u) & 31);
+                v[u] = (col_ok && j + u < cnt) ? __ldcg(reinterpret_cast<const float4*>(Op + (long long)sidx * B * D))
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j + u >= cnt) ww[u] = 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                acc.x = fmaf(ww[u], v[u].x, acc.x); acc.y = fmaf(ww[u], v[u].y, acc.y);
+                acc.z = fmaf(ww[u], v[u].z, acc.z); acc.w = fmaf(ww[u], v[u].w, acc.w);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i + 1 < kMaxPer; ++i) w[i] = w[i + 1];
+    }
+    if (fin) {
+        if (col_ok) {
+            const float sc = f.inv_T * f.dq_scale, il = 1.0f / l_tot;
+            float4 o;
+            o.x = ((acc.x + wpos * kv.x) * il - kv.x) * sc; o.y = ((acc.y + wpos * kv.y) * il - kv.y) * sc;
+            o.z = ((acc.z + wpos * kv.z) * il - kv.z) * sc; o.w = ((acc.w + wpos * kv.w) * il - kv.w) * sc;
+            *reinterpret_cast<float4*>(f.dq + (long long)row * D + 4 * lane) = o;
+        }
+        if (lane == 0) {
+            f.loss_rows[row] = logf(l_tot) + mstar - pos;
+            f.pos_is_max[row] = pos >= mtrue ? 1 : 0;
+            if (f.max_logit) f.max_logit[row] = fmaxf(pos, mtrue);
+        }
+    } else {
+        float* rec = f.packed + (long long)row * (D + 4);
+        if (col_ok) *reinterpret_cast<float4*>(rec + 4 * lane) = acc;
+        if (lane == 0) *reinterpret_cast<float4*>(rec + D) = make_float4(mref, l_tot, mtrue, 0.f);
+    }
+}
+
 template <int D, bool kPoly, bool kRagged>
 __global__ void __launch_bounds__(384, 1)
 nce_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                int B, long long K_local, float scale_log2, int n_splits, float* __restrict__ part_m,
                float* __restrict__ part_l, float* __restrict__ part_mmax, float* __restrict__ part_O,
-               float* __restrict__ dbg_S, int hook_arg) {
+               float* __restrict__ dbg_S, int hook_arg, const NceFuse fuse) {
     using C = Cfg3<D>;
     constexpr int BN = C::BN;
     extern __shared__ uint8_t smem_raw[];
@@ -874,6 +976,44 @@ nce_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             part_l[orow] = l_half + bars->lsum[rit];
         }
         if (warp == 4 && lane == 0) LIFE(10);
+        if (fuse.mode != kFuseNone) {
+            // ---- in-kernel combine: ticket on this query tile, wait for its other splits, combine a slice of its rows
+            const int tid = threadIdx.x - 128;
+            __threadfence();                                  // this thread's partial stores are visible device-wide
+            group_barrier(5, 256);
+            if (tid == 0) {
+                atomicAdd(&fuse.counters[mt], 1u);
+                const long long t_start = clock64();
+                while (ld_acquire_u32(&fuse.counters[mt]) < (unsigned)n_splits) {
+                    __nanosleep(40);
+                    if (clock64() - t_start > 4000000000ll) { atomicExch(&g_tc_error, 501); __trap(); }
+                }
+            }
+            group_barrier(5, 256);
+            __threadfence();
+            const int w8 = warp - 4;                          // 0..7
+            for (int r = split + w8 * n_splits; r < kBM; r += 8 * n_splits)
+                if (row_base + r < B)
+                    fuse_combine_row<D>(fuse, row_base + r, B, n_splits, part_m, part_l, part_mmax, part_O, lane);
+            // ---- last CTA of the grid: mean loss / accuracy, counters back to zero
+            __threadfence();
+            group_barrier(5, 256);
+            const unsigned total = gridDim.x * gridDim.y;
+            if (tid == 0) bars->pad = atomicAdd(&fuse.counters[gridDim.x], 1u) == total - 1 ? 1u : 0u;
+            group_barrier(5, 256);
+            if (bars->pad != 0u) {
+                __threadfence();
+                if (w8 == 0) {
+                    if (fuse.mode == kFuseFinal && fuse.loss_mean != nullptr) {
+                        float sl = 0.f, sa = 0.f;
+                        for (int i = lane; i < B; i += 32) { sl += __ldcg(fuse.loss_rows + i); sa += (float)__ldcg(fuse.pos_is_max + i); }
+                        sl = warp_sum(sl); sa = warp_sum(sa);
+                        if (lane == 0) { *fuse.loss_mean = sl / (float)B; *fuse.acc_pct = sa * (100.0f / (float)B); }
+                    }
+                    for (int i = lane; i <= (int)gridDim.x; i += 32) fuse.counters[i] = 0u;
+                }
+            }
+        }
     }
 
     tc_fence_before();
@@ -959,7 +1099,7 @@ static bool use_poly_exp() {     // MOMA_B200_NCE_POLY=1: 25 % of the exp2 on th
 
 template <int D, bool kPoly, bool kRagged>
 static int launch3(const void* q, const void* queue, int64_t B, int64_t K_local, float inv_T, int n_splits,
-                   float* pm, float* pl, float* pmm, float* pO, float* dbg, cudaStream_t st) {
+                   float* pm, float* pl, float* pmm, float* pO, float* dbg, cudaStream_t st, const NceFuse& fuse) {
     using C = Cfg3<D>;
     CUtensorMap mq, mk;
     int rc = cached_map(&mq, q, B, D, kBM);
@@ -976,20 +1116,20 @@ static int launch3(const void* q, const void* queue, int64_t B, int64_t K_local,
     int hooks = 0;
     if (kAblateHooks) { const char* e = getenv("MOMA_TC_ABLATE"); hooks = e ? atoi(e) : 0; }
     launch_pdl(nce_tc3_kernel<D, kPoly, kRagged>, grid, dim3(C::THREADS), (size_t)C::SMEM_TOTAL, st, mq, mk, (int)B, (long long)K_local,
-               scale_log2, n_splits, pm, pl, pmm, pO, dbg, hooks);
+               scale_log2, n_splits, pm, pl, pmm, pO, dbg, hooks, fuse);
     MOMA_CUDA_LAUNCH_CHECK("nce_partial(bf16/tcgen05 v3)");
     note_launches(1);
     return MOMA_OK;
 }
 template <int D>
 static int launch2(const void* q, const void* queue, int64_t B, int64_t K_local, float inv_T, int n_splits,
-                   float* pm, float* pl, float* pmm, float* pO, float* dbg, cudaStream_t st) {
+                   float* pm, float* pl, float* pmm, float* pO, float* dbg, cudaStream_t st, const NceFuse& fuse = NceFuse{}) {
     const bool ragged = (K_local % 128) != 0;
     if (use_poly_exp())
-        return ragged ? launch3<D, true, true>(q, queue, B, K_local, inv_T, n_splits, pm, pl, pmm, pO, dbg, st)
-                      : launch3<D, true, false>(q, queue, B, K_local, inv_T, n_splits, pm, pl, pmm, pO, dbg, st);
-    return ragged ? launch3<D, false, true>(q, queue, B, K_local, inv_T, n_splits, pm, pl, pmm, pO, dbg, st)
-                  : launch3<D, false, false>(q, queue, B, K_local, inv_T, n_splits, pm, pl, pmm, pO, dbg, st);
+        return ragged ? launch3<D, true, true>(q, queue, B, K_local, inv_T, n_splits, pm, pl, pmm, pO, dbg, st, fuse)
+                      : launch3<D, true, false>(q, queue, B, K_local, inv_T, n_splits, pm, pl, pmm, pO, dbg, st, fuse);
+    return ragged ? launch3<D, false, true>(q, queue, B, K_local, inv_T, n_splits, pm, pl, pmm, pO, dbg, st, fuse)
+                  : launch3<D, false, false>(q, queue, B, K_local, inv_T, n_splits, pm, pl, pmm, pO, dbg, st, fuse);
 }
 
 template <int D, int NQ, int BN>
@@ -1052,6 +1192,33 @@ int nce_tc_num_splits(int64_t B, int64_t D, int64_t K_local) {
     if (s > tiles / min_tiles) s = tiles / min_tiles;
     if (s < 1) s = 1;
     return (int)s;
+}
+
+
+// ---- one-launch InfoNCE (tcgen05 partial pass + in-kernel combine); D in {64, 128}
+bool nce_fused_supported(int64_t B, int64_t D, int64_t K_local) {
+    if (!(D == 64 || D == 128) || B <= 0 || K_local <= 0) return false;
+    const int s = nce_tc_num_splits(B, D, K_local);
+    const int64_t mt = (B + tc::kBM - 1) / tc::kBM;
+    // every CTA of the grid must be co-resident (they wait for each other) and every split must own at least one tile
+    return s <= 160 && mt * s <= sm_count() && s <= (K_local + 127) / 128;
+}
+size_t nce_fused_workspace_floats(int64_t B, int64_t D, int64_t K_local) {
+    const int64_t s = nce_tc_num_splits(B, D, K_local);
+    return (size_t)(3 * s * B + s * B * D);
+}
+int nce_fused_launch(const void* q_bf16, const void* queue_bf16, int64_t B, int64_t D, int64_t K_local, float inv_T,
+                     float* workspace, const tc::NceFuse& fuse, cudaStream_t stream) {
+    const int s = nce_tc_num_splits(B, D, K_local);
+    float* pm = workspace;
+    float* pl = pm + (int64_t)s * B;
+    float* pmm = pl + (int64_t)s * B;
+    float* pO = pmm + (int64_t)s * B;
+    MOMA_REQUIRE((reinterpret_cast<uintptr_t>(q_bf16) & 127) == 0 && (reinterpret_cast<uintptr_t>(queue_bf16) & 127) == 0,
+                 MOMA_ERR_ALIGN, "nce_fused: q / queue must be 128-byte aligned for TMA");
+    MOMA_REQUIRE(aligned16(pO), MOMA_ERR_ALIGN, "nce_fused: workspace must be 16-byte aligned");
+    if (D == 64) return tc::launch2<64>(q_bf16, queue_bf16, B, K_local, inv_T, s, pm, pl, pmm, pO, nullptr, stream, fuse);
+    return tc::launch2<128>(q_bf16, queue_bf16, B, K_local, inv_T, s, pm, pl, pmm, pO, nullptr, stream, fuse);
 }
 
 int nce_tc_partial(const void* q, const void* queue, int64_t B, int64_t D, int64_t K_local, float inv_T,

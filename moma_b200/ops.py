@@ -255,6 +255,62 @@ def nce_combine_packed(packed: torch.Tensor, q_f32: torch.Tensor, k_f32: torch.T
     return rows, dq, pim, mx, fin[0], fin[1:2]
 
 
+# ---- one-launch InfoNCE (tcgen05 pass + in-kernel combine) ---------------------------------------------------------
+_FUSE_COUNTERS = {}
+
+
+def _fuse_counters(device) -> torch.Tensor:
+    """A zeroed block of 256 uint32 ticket counters for one launch.  The kernel leaves its block zero; consecutive
+    launches rotate through 16 blocks per device so that launches running concurrently on different streams (parallel
+    graph branches, the dual-queue variants) never share one."""
+    ent = _FUSE_COUNTERS.get(device)
+    if ent is None:
+        ent = _FUSE_COUNTERS[device] = [torch.zeros((16, 256), dtype=torch.int32, device=device), 0]
+    ent[1] = (ent[1] + 1) % 16
+    return ent[0][ent[1]]
+
+
+def nce_fused_enabled(B: int, D: int, K_local: int) -> bool:
+    """MOMA_B200_NCE_FUSED=0 falls back to the three-launch path (partial, combine, finalize): A/B switch."""
+    if os.environ.get("MOMA_B200_NCE_FUSED", "1") == "0":
+        return False
+    return bool(_lib.load().moma_nce_fused_supported(B, D, K_local))
+
+
+def nce_fused(q_bf16: torch.Tensor, queue_bf16: torch.Tensor, q_f32: torch.Tensor, k_f32: torch.Tensor, inv_T: float,
+              round_bf16: bool, dq_scale: float):
+    """(rows, dq, pos_is_max, max_logit, loss_mean, acc_pct) from ONE kernel launch."""
+    lib = _lib.load()
+    B, D = q_bf16.shape
+    K_local = queue_bf16.shape[0]
+    dev = q_bf16.device
+    nbytes = int(lib.moma_nce_fused_workspace_bytes(B, D, K_local))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    rows = torch.empty(B, dtype=torch.float32, device=dev)
+    dq = torch.empty((B, D), dtype=torch.float32, device=dev)
+    pim = torch.empty(B, dtype=torch.int32, device=dev)
+    mx = torch.empty(B, dtype=torch.float32, device=dev)
+    fin = torch.empty(2, dtype=torch.float32, device=dev)
+    check(lib.moma_nce_fused(_p(q_bf16), _p(queue_bf16), _p(q_f32), _p(k_f32), B, D, K_local, inv_T, int(round_bf16),
+                             float(dq_scale), _p(ws), nbytes, _p(_fuse_counters(dev)), _p(rows), _p(dq), _p(pim), _p(mx),
+                             _p(fin), fin.data_ptr() + 4, _stream()))
+    return rows, dq, pim, mx, fin[0], fin[1:2]
+
+
+def nce_fused_packed(q_bf16: torch.Tensor, queue_bf16: torch.Tensor, inv_T: float) -> torch.Tensor:
+    """Merged packed records [B, D + 4] = (O | m | l | mmax | pad) of q against the local queue rows, one launch."""
+    lib = _lib.load()
+    B, D = q_bf16.shape
+    K_local = queue_bf16.shape[0]
+    dev = q_bf16.device
+    nbytes = int(lib.moma_nce_fused_workspace_bytes(B, D, K_local))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    packed = torch.empty((B, D + 4), dtype=torch.float32, device=dev)
+    check(lib.moma_nce_fused_packed(_p(q_bf16), _p(queue_bf16), B, D, K_local, inv_T, _p(ws), nbytes,
+                                    _p(_fuse_counters(dev)), _p(packed), _stream()))
+    return packed
+
+
 def nce_operands(q: torch.Tensor, k: torch.Tensor, precision: str):
     """Operands of the chosen mode: (q_op, dtype, q_f32, k_f32, round_bf16).  In bf16 mode the
     partial kernel reads a bf16 copy of q; the combine kernel rounds q / k inline (round_bf16)."""
@@ -303,7 +359,7 @@ class _NceFused(torch.autograd.Function):
         return (None if grad is None else grad.to(ctx.q_dtype)), None, None
 
 
-def nce_fused(q: torch.Tensor, k: torch.Tensor, compute) -> NceOut:
+def nce_autograd(q: torch.Tensor, k: torch.Tensor, compute) -> NceOut:
     return NceOut(*_NceFused.apply(q, k.detach(), compute))
 
 
@@ -319,11 +375,14 @@ def nce_rows(q: torch.Tensor, k: torch.Tensor, queue_f32: torch.Tensor, queue_bf
     def compute(q_, k_):
         q_op, dtype, q32, k32, rnd = nce_operands(q_, k_, precision)
         queue = queue_bf16 if dtype == BF16 else queue_f32
+        if dtype == BF16 and nce_fused_enabled(q_op.shape[0], q_op.shape[1], queue.shape[0]):
+            rows, dq, pim, mx, loss, acc = nce_fused(q_op, queue, q32, k32, inv_T, rnd, 1.0 / q_.shape[0])
+            return loss, rows, pim, mx, acc, dq
         stats, O = nce_partial(q_op, queue, inv_T, dtype)
         rows, dq, pim, mx, loss, acc = nce_combine(stats, O, q32, k32, inv_T, rnd, 1.0 / q_.shape[0], want_mean=True)
         return loss, rows, pim, mx, acc, dq
 
-    return nce_fused(q, k, compute)
+    return nce_autograd(q, k, compute)
 
 
 def bf16_supported(D: int) -> bool:

@@ -180,8 +180,11 @@ class ShardedMoCo(BaseMoCo):
                 dist.all_gather_into_tensor(all_q, q_op.contiguous(), group=group)
             # 2. local pass over this rank's K / W rows for all n queries, then fold the splits
             queue = shadow if use_bf16 else memory_shard
-            stats, Opart = ops.nce_partial(all_q, queue, inv_T, dtype)
-            packed = ops.nce_merge_packed(stats, Opart)                 # [n, D + 4] = (O | m | l | mmax | pad)
+            if use_bf16 and ops.nce_fused_enabled(all_q.shape[0], D, queue.shape[0]):
+                packed = ops.nce_fused_packed(all_q, queue, inv_T)       # pass + merge of the K-splits in ONE launch
+            else:
+                stats, Opart = ops.nce_partial(all_q, queue, inv_T, dtype)
+                packed = ops.nce_merge_packed(stats, Opart)             # [n, D + 4] = (O | m | l | mmax | pad)
             # 3. exchange: rows are ordered by owner rank, so the records route with one all-to-all
             if peer is not None:
                 recv = peer.alltoall(packed.view(W, bsz, D + 4), CH_PARTIALS)
@@ -191,7 +194,7 @@ class ShardedMoCo(BaseMoCo):
             rows, dq, pim, mx, loss, acc = ops.nce_combine_packed(recv, q32, k32, inv_T, rnd, 1.0 / bsz)
             return loss, rows, pim, mx, acc, dq
 
-        nce = ops.nce_fused(q, k, compute)
+        nce = ops.nce_autograd(q, k, compute)
         shape = (bsz, self.K + 1) if bsz != 1 else (self.K + 1,)
         logits = LazyLogits(shape, q.device, nce, labels, _stale_after_enqueue)
         if not defer_enqueue:

@@ -317,3 +317,40 @@ def test_emulated_shards_through_a_captured_graph(bf16, W):
     # and against the replicated single pass over the whole queue
     nce = ops.nce_rows(q32, k32, queue, queue.to(torch.bfloat16), T, "bf16")
     assert abs(loss.item() - nce.loss.item()) < 5e-4 * abs(loss_o)
+
+
+# ------------------------------------------------------------------ one-launch InfoNCE (in-kernel combine)
+@pytest.mark.parametrize("B,D,K", [(256, 128, 16384), (512, 128, 65536), (200, 128, 1000), (512, 64, 8192), (128, 128, 128)])
+def test_fused_nce_equals_three_launch_path_and_oracle(bf16, B, D, K):
+    """moma_nce_fused (tcgen05 pass + combine + finalize in ONE launch) against moma_nce_partial + moma_nce_combine on
+    the same operands, and against the oracle fed the bf16-rounded operands; repeated launches (the ticket counters
+    must come back to zero), ragged K and a partial last query tile included."""
+    from moma_b200 import _lib, ops
+    from moma_b200._lib import BF16
+    lib = _lib.load()
+    torch.manual_seed(B + K)
+    T = 0.15
+    q = torch.randn(B, D, device="cuda") * 0.5
+    k = torch.randn(B, D, device="cuda") * 0.5
+    queue = torch.nn.functional.normalize(torch.randn(K, D, device="cuda"))
+    q16, queue16 = q.to(torch.bfloat16), queue.to(torch.bfloat16)
+    assert lib.moma_nce_fused_supported(B, D, K) == 1
+    stats, Op = ops.nce_partial(q16, queue16, 1 / T, BF16)
+    rows0, dq0, pim0, mx0, loss0, acc0 = ops.nce_combine(stats, Op, q, k, 1 / T, True, 1.0 / B, want_mean=True)
+    for rep in range(3):
+        rows, dq, pim, mx, loss, acc = ops.nce_fused(q16, queue16, q, k, 1 / T, True, 1.0 / B)
+        torch.cuda.synchronize()
+        assert torch.allclose(rows, rows0, rtol=2e-6, atol=1e-6), rep
+        assert torch.allclose(dq, dq0, rtol=1e-5, atol=1e-9), rep
+        assert torch.equal(pim, pim0) and torch.allclose(mx, mx0, rtol=1e-6)
+        assert abs(loss.item() - loss0.item()) < 2e-6 * abs(loss0.item()) and acc.item() == acc0.item()
+    assert int(ops._FUSE_COUNTERS[q.device][0].abs().sum().item()) == 0          # every block back to zero
+    r_ = lambda t: O.round_bf16(npy(t)).astype(np.float64)
+    loss_o, rows_o, dq_o, pim_o = O.nce_loss_and_grad(r_(q), r_(k), r_(queue), T)
+    assert abs(loss.item() - loss_o) < 1e-3 * abs(loss_o) and rel(npy(dq), dq_o) < 1e-3
+    assert np.array_equal(npy(pim).astype(bool), pim_o)
+    # the packed variant == partial + merge_packed
+    packed = ops.nce_fused_packed(q16, queue16, 1 / T)
+    want = ops.nce_merge_packed(stats, Op)
+    torch.cuda.synchronize()
+    assert torch.allclose(packed[:, :D + 3], want[:, :D + 3], rtol=1e-5, atol=1e-9)
