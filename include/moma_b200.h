@@ -111,6 +111,9 @@ int moma_enqueue_ids(int64_t n, int64_t index, const int64_t *index_dev, int64_t
 int moma_pointer_advance(int64_t *index_dev, int64_t n, int64_t K, moma_stream_t stream);
 /* fp32 -> bf16 (round to nearest even); used to (re)build the queue shadow. */
 int moma_cast_bf16(const float *src, void *dst_bf16, int64_t numel, moma_stream_t stream);
+/* y = x * (*scalar_dev): chain rule of the fused InfoNCE gradient with the upstream scalar (the autograd backward of
+ * learning/contrast_trainer.py:197 inside helper/loops_moma.py:345-360), device-resident scalar, no host sync. */
+int moma_scale_by_scalar(const float *x, const float *scalar_dev, float *y, int64_t numel, moma_stream_t stream);
 
 /* ------------------------------------------------------------------------- *
  * (a) InfoNCE logits + cross-entropy forward AND backward in one pass

@@ -32,6 +32,7 @@ SIGNATURES = {
     "moma_enqueue_ids": (c_int, [_i64, _i64, _vp, _i64, _vp, _vp]),
     "moma_pointer_advance": (c_int, [_vp, _i64, _i64, _vp]),
     "moma_cast_bf16": (c_int, [_vp, _vp, _i64, _vp]),
+    "moma_scale_by_scalar": (c_int, [_vp, _vp, _vp, _i64, _vp]),
     "moma_nce_num_splits": (c_int, [_i64, _i64, _i64, c_int]),
     "moma_nce_partial": (c_int, [_vp, _vp, _i64, _i64, _i64, c_float, c_int, c_int, _vp, _vp, _vp, _vp, _vp]),
     "moma_nce_combine": (c_int, [_vp, _vp, _vp, _vp, c_int, _vp, _vp, _i64, _i64, c_float, c_int, c_float,

@@ -7,7 +7,8 @@ On the B200 path:
   * ``_global_gather``   -> ``all_gather_into_tensor`` straight into the [W*B, D] result
                             (reference :83-88: W ``ones_like`` allocations + ``cat``);
   * ``_compute_loss_accuracy`` -> served by the LazyLogits handle, no [B, K+1] passes, no host sync.
-``_shuffle_bn`` keeps the reference's collective sequence (it sits before the path).
+``_shuffle_bn`` exchanges image SLICES (one all-to-all) instead of all-gathering the node's images (SURVEY 8f-1);
+its permutation, its returned (k, all_k) and the batches the momentum encoder sees are the reference's.
 """
 from __future__ import annotations
 
@@ -179,6 +180,36 @@ class ContrastTrainer(BaseTrainer):
         dist.all_gather_into_tensor(out, x)
         return out
 
+    # ---- ShuffleBN (reference :90-133) -----------------------------------------------------------------------
+    # The reference all-gathers the INPUT IMAGES of the node (W x B x 3 x H x W: 38.5 MB per rank and step at
+    # 64 x 3 x 224^2, 201 MB at 512^2) and then keeps the B rows its slice of the shared permutation names.  A rank only
+    # needs those B images: with the permutation known everywhere, each rank sends every peer exactly the rows that
+    # peer will feed to its momentum encoder (one all-to-all of image slices, (W-1)/W of B images per rank instead of
+    # (W-1) x B received), and the result is bit-identical to ``node_x[this_ids]``.  The permutation itself is drawn
+    # exactly as the reference draws it (torch.randperm on the host RNG, rank 0's draw broadcast), so the RNG streams and
+    # the batches the momentum encoder's train-mode BatchNorm sees are the reference's.
+    # MOMA_B200_SHUFFLE_BN=gather restores the reference's image all-gather (A/B switch).
+    @staticmethod
+    def _exchange_shuffled_rows(x, shuffle_ids_host, rank, world, bsz, group):
+        """rows ``node_x[shuffle_ids[rank * bsz:(rank + 1) * bsz]]`` of the (never materialised) node batch
+        ``node_x = cat(x of every rank)``, via one all-to-all of row slices."""
+        ids = shuffle_ids_host.view(world, bsz)                  # ids[r] = the node rows rank r consumes, in its order
+        owner = ids // bsz                                       # which rank holds each of them
+        send_idx, in_splits = [], []
+        for r in range(world):                                   # what I send to r: my rows among ids[r], in r's order
+            mine = ids[r][owner[r] == rank] % bsz
+            send_idx.append(mine)
+            in_splits.append(int(mine.numel()))
+        out_splits = [int((owner[rank] == s).sum()) for s in range(world)]
+        send = x.index_select(0, torch.cat(send_idx).to(x.device))
+        recv = torch.empty((bsz,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_to_all_single(recv, send, output_split_sizes=out_splits, input_split_sizes=in_splits, group=group)
+        # recv is grouped by source rank; put every row at its position in this rank's order
+        pos = torch.cat([torch.nonzero(owner[rank] == s).flatten() for s in range(world)]).to(x.device)
+        out = torch.empty_like(recv)
+        out.index_copy_(0, pos, recv)
+        return out
+
     def _shuffle_bn(self, x, model_ema, model_ema_head):
         """Shuffle-BN teacher forward (reference :90-133): returns (k, all_k)."""
         args = self.args
@@ -186,17 +217,20 @@ class ContrastTrainer(BaseTrainer):
         bsz = x.size(0)
         wl = dist.get_world_size(local_gp)
         x = x.contiguous()
-        node_x = torch.empty((wl * bsz,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
-        dist.all_gather_into_tensor(node_x, x, group=local_gp)
+        sliced = wl > 1 and os.environ.get("MOMA_B200_SHUFFLE_BN", "slices") != "gather"
 
-        shuffle_ids = torch.randperm(bsz * wl).to(x.device)
+        shuffle_ids = torch.randperm(bsz * wl).to(x.device)      # same host-RNG draw as the reference (:108-110)
         reverse_ids = torch.argsort(shuffle_ids)
         dist.broadcast(shuffle_ids, 0)
         dist.broadcast(reverse_ids, 0)
 
-        this_ids = shuffle_ids[args.local_rank * bsz:(args.local_rank + 1) * bsz]
         with torch.no_grad():
-            this_x = node_x[this_ids]
+            if sliced:
+                this_x = self._exchange_shuffled_rows(x, shuffle_ids.cpu(), args.local_rank, wl, bsz, local_gp)
+            else:
+                node_x = torch.empty((wl * bsz,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+                dist.all_gather_into_tensor(node_x, x, group=local_gp)
+                this_x = node_x[shuffle_ids[args.local_rank * bsz:(args.local_rank + 1) * bsz]]
             feat_t, logit_t = model_ema(this_x, is_feat=True)
             k = model_ema_head(feat_t[-1])
 

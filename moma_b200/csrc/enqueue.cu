@@ -251,3 +251,35 @@ extern "C" __attribute__((visibility("default"))) int moma_cast_bf16(const float
     note_launches(1);
     return MOMA_OK;
 }
+
+// y = x * (*scalar): the chain-rule multiply of the fused InfoNCE gradient by the upstream scalar (d total / d loss_kd,
+// a device-resident 0-dim tensor -- opt.beta times whatever follows, helper/loops_moma.py:345) without a host sync and
+// inside the step's chain of programmatic dependent launches.
+__global__ void __launch_bounds__(256) scale_by_scalar_kernel(const float* __restrict__ x, const float* __restrict__ scalar,
+                                                              float* __restrict__ y, int64_t nvec, int64_t numel) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const float s = *scalar;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        float4 v = reinterpret_cast<const float4*>(x)[i];
+        v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+        reinterpret_cast<float4*>(y)[i] = v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (numel & 3)) y[(nvec << 2) + threadIdx.x] = x[(nvec << 2) + threadIdx.x] * s;
+}
+extern "C" __attribute__((visibility("default"))) int moma_scale_by_scalar(const float* x, const float* scalar_dev, float* y, int64_t numel,
+                                                                          moma_stream_t stream) {
+    MOMA_REQUIRE(numel >= 0 && (numel == 0 || (x && scalar_dev && y)), MOMA_ERR_INVALID, "scale_by_scalar: bad arguments");
+    MOMA_REQUIRE(aligned16(x) && aligned16(y), MOMA_ERR_ALIGN, "scale_by_scalar: unaligned pointers");
+    if (numel == 0) return MOMA_OK;
+    const int64_t nvec = numel >> 2;
+    int64_t blocks = (nvec + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    launch_pdl(scale_by_scalar_kernel, dim3((unsigned)blocks), dim3(256), 0, as_stream(stream), x, scalar_dev, y, nvec, numel);
+    MOMA_CUDA_LAUNCH_CHECK("scale_by_scalar");
+    note_launches(1);
+    return MOMA_OK;
+}

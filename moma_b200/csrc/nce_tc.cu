@@ -611,19 +611,22 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
 }
 __device__ __forceinline__ float bf16_rne(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
-// One warp combines one row.  Lane `lane` owns columns [4 * lane, 4 * lane + 4) (lanes >= D / 4 idle along the columns).
+// `wpr` warps combine one row: warp `sub` of them takes the splits sub, sub + wpr, ... (8 independent 128-bit loads in
+// flight per lane and batch), the partial sums meet in shared memory and warp 0 of the row finishes in a fixed order
+// (deterministic).  Lane `lane` owns columns [4 * lane, 4 * lane + 4).  `red`: [8 warps][33] float4 scratch.
 template <int D>
 __device__ __forceinline__ void fuse_combine_row(const NceFuse& f, int row, int B, int n_splits, const float* part_m,
-                                                 const float* part_l, const float* part_mmax, const float* part_O, int lane) {
+                                                 const float* part_l, const float* part_mmax, const float* part_O, int lane,
+                                                 int sub, int wpr, int slot0, float4* red, int bar_id) {
     constexpr int kMaxPer = 5;                         // n_splits <= 160
-    float ms[kMaxPer], w[kMaxPer];
     float mref = -CUDART_INF_F, mtrue = -CUDART_INF_F;
 #pragma unroll
     for (int i = 0; i < kMaxPer; ++i) {
         const int sidx = lane + 32 * i;
-        ms[i] = sidx < n_splits ? __ldcg(part_m + (long long)sidx * B + row) : -CUDART_INF_F;
-        const float mt_ = sidx < n_splits ? __ldcg(part_mmax + (long long)sidx * B + row) : -CUDART_INF_F;
-        mref = fmaxf(mref, ms[i]); mtrue = fmaxf(mtrue, mt_);
+        if (sidx < n_splits) {
+            mref = fmaxf(mref, __ldcg(part_m + (long long)sidx * B + row));
+            mtrue = fmaxf(mtrue, __ldcg(part_mmax + (long long)sidx * B + row));
+        }
     }
     mref = warp_max(mref); mtrue = warp_max(mtrue);
     const bool fin = f.mode == kFuseFinal;
@@ -644,41 +647,46 @@ __device__ __forceinline__ void fuse_combine_row(const NceFuse& f, int row, int 
         pos = warp_sum(dot) * f.inv_T;
     }
     const float mstar = fin ? fmaxf(mref, pos) : mref;
-    const float wpos = fin ? expf(pos - mstar) : 0.f;
-    float lsum = 0.f;
-#pragma unroll
-    for (int i = 0; i < kMaxPer; ++i) {
-        const int sidx = lane + 32 * i;
-        w[i] = (sidx < n_splits && ms[i] > -CUDART_INF_F) ? expf(ms[i] - mstar) : 0.f;
-        if (sidx < n_splits) lsum += w[i] * __ldcg(part_l + (long long)sidx * B + row);
-    }
-    const float l_tot = warp_sum(lsum) + wpos;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float lsum = 0.f;
     const float* Op = part_O + (long long)row * D + 4 * lane;
-    for (int s0 = 0; s0 < n_splits; s0 += 32) {
-        const float wl = w[0];                         // rotated below: w[0] always holds the weights of splits s0 .. s0 + 31
-        const int cnt = min(32, n_splits - s0);
-        for (int j = 0; j < cnt; j += 4) {             // 4 independent 128-bit loads in flight per lane
-            float4 v[4];
-            float ww[4];
+    for (int s0 = sub; s0 < n_splits; s0 += 8 * wpr) {
+        float4 v[8];
+        float ms[8], ls[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int sidx = s0 + j + u;
-                ww[u] = __shfl_sync(0xffffffffu, wl, (j + u) & 31);
-                v[u] = (col_ok && j + u < cnt) ? __ldcg(reinterpret_cast<const float4*>(Op + (long long)sidx * B * D))
-                                               : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (j + u >= cnt) ww[u] = 0.f;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                acc.x = fmaf(ww[u], v[u].x, acc.x); acc.y = fmaf(ww[u], v[u].y, acc.y);
-                acc.z = fmaf(ww[u], v[u].z, acc.z); acc.w = fmaf(ww[u], v[u].w, acc.w);
-            }
+        for (int u = 0; u < 8; ++u) {
+            const int sidx = s0 + u * wpr;
+            const bool ok = sidx < n_splits;
+            ms[u] = ok ? __ldcg(part_m + (long long)sidx * B + row) : -CUDART_INF_F;
+            ls[u] = ok ? __ldcg(part_l + (long long)sidx * B + row) : 0.f;
+            v[u] = (ok && col_ok) ? __ldcg(reinterpret_cast<const float4*>(Op + (long long)sidx * B * D))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int i = 0; i + 1 < kMaxPer; ++i) w[i] = w[i + 1];
+        for (int u = 0; u < 8; ++u) {
+            const float w = ms[u] > -CUDART_INF_F ? expf(ms[u] - mstar) : 0.f;
+            lsum = fmaf(w, ls[u], lsum);
+            acc.x = fmaf(w, v[u].x, acc.x); acc.y = fmaf(w, v[u].y, acc.y);
+            acc.z = fmaf(w, v[u].z, acc.z); acc.w = fmaf(w, v[u].w, acc.w);
+        }
+    }
+    // meet in shared memory: slot0 + sub is this warp's scratch row; element 32 carries the row-sum share
+    float4* mine = red + (slot0 + sub) * 33;
+    mine[lane] = acc;
+    if (lane == 0) mine[32] = make_float4(lsum, 0.f, 0.f, 0.f);
+    if (wpr > 1) asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 * wpr) : "memory");
+    else __syncwarp();
+    if (sub != 0) return;
+    float l_tot = 0.f;
+    acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < wpr; ++j) {
+        const float4 o = red[(slot0 + j) * 33 + lane];
+        acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+        l_tot += red[(slot0 + j) * 33 + 32].x;
     }
     if (fin) {
+        const float wpos = expf(pos - mstar);
+        l_tot += wpos;
         if (col_ok) {
             const float sc = f.inv_T * f.dq_scale, il = 1.0f / l_tot;
             float4 o;
@@ -992,9 +1000,21 @@ nce_tc3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             group_barrier(5, 256);
             __threadfence();
             const int w8 = warp - 4;                          // 0..7
-            for (int r = split + w8 * n_splits; r < kBM; r += 8 * n_splits)
-                if (row_base + r < B)
-                    fuse_combine_row<D>(fuse, row_base + r, B, n_splits, part_m, part_l, part_mmax, part_O, lane);
+            {
+                // rows of this CTA's slice: split, split + n_splits, ... (< 128 and < B); `wpr` warps per row
+                int n_rows = 0;
+                for (int r = split; r < kBM && row_base + r < B; r += n_splits) ++n_rows;
+                float4* red = reinterpret_cast<float4*>(stage);          // the staging area is free again (>= 8 x 33 float4)
+                for (int j0 = 0; j0 < n_rows; j0 += 8) {
+                    const int g = min(8, n_rows - j0);                   // rows handled in this round
+                    const int wpr = g == 1 ? 8 : (g == 2 ? 4 : (g <= 4 ? 2 : 1));
+                    const int rj = w8 / wpr, sub = w8 % wpr;
+                    if (rj < g)
+                        fuse_combine_row<D>(fuse, row_base + split + (j0 + rj) * n_splits, B, n_splits, part_m, part_l,
+                                            part_mmax, part_O, lane, sub, wpr, rj * wpr, red, 6 + rj);
+                    group_barrier(5, 256);                               // scratch reuse between rounds
+                }
+            }
             // ---- last CTA of the grid: mean loss / accuracy, counters back to zero
             __threadfence();
             group_barrier(5, 256);

@@ -352,7 +352,12 @@ class _NceFused(torch.autograd.Function):
         (dq_mean,) = ctx.saved_tensors
         grad = None
         if g_loss is not None:
-            grad = dq_mean * g_loss
+            if (g_loss.is_cuda and g_loss.numel() == 1 and g_loss.dtype == torch.float32 and dq_mean.is_contiguous()
+                    and not torch.is_grad_enabled()):
+                grad = torch.empty_like(dq_mean)          # one PDL-chained launch instead of a broadcasting torch multiply
+                check(_lib.load().moma_scale_by_scalar(_p(dq_mean), _p(g_loss), _p(grad), dq_mean.numel(), _stream()))
+            else:
+                grad = dq_mean * g_loss
         if g_rows is not None:
             gr = (g_rows.unsqueeze(1) * dq_mean) * float(ctx.B)
             grad = gr if grad is None else grad + gr
@@ -484,6 +489,7 @@ class _Attention(torch.autograd.Function):
         ctx.save_for_backward(xc, wq, wp, qkv, o, lse)
         ctx.H = H
         ctx.has_bq = b_qkv is not None
+        ctx.set_materialize_grads(False)      # no zero-fill kernel for the (non-differentiable) second output's gradient
         if want_probs:
             ctx.mark_non_differentiable(probs)
             return y, probs
@@ -498,6 +504,8 @@ class _Attention(torch.autograd.Function):
         xc, wq, wp, qkv, o, lse = ctx.saved_tensors
         N, C = xc.shape
         H = ctx.H
+        if gy is None:                        # the output was not used downstream
+            return (None,) * 8
         gy = _f32c(gy)
         need = ctx.needs_input_grad
         dev = xc.device

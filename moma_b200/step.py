@@ -21,6 +21,7 @@ and tests/ all drive this one object.
 """
 from __future__ import annotations
 
+import os
 from argparse import Namespace
 
 import torch
@@ -82,6 +83,7 @@ class CriterionStep:
             self.host_s, self.host_t = self.host_s.pin_memory(), self.host_t.pin_memory()
         self.h2d_bytes = (self.host_s.numel() + self.host_t.numel()) * 4
         self.loss = self.acc = None
+        self._unit = None
         self.last = {}                                # tensors of the latest step, for the parity self-check
 
     # ------------------------------------------------------------------ keys of the step
@@ -141,7 +143,11 @@ class CriterionStep:
                     self.contrast.enqueue(owned_k=owned_k)
                 else:
                     self.contrast.enqueue(all_k)
-        losses[0].backward()
+        # loss.backward() as at helper/loops_moma.py:360; the unit upstream gradient is a preallocated device scalar
+        # (autograd would otherwise launch a fill kernel for it every step)
+        if self._unit is None:
+            self._unit = torch.ones((), dtype=torch.float32, device=self.dev)
+        losses[0].backward(gradient=self._unit)
         self.loss, self.acc = losses[0], accs[0]
         self.last = {"q": f_s, "k": k, "all_k": all_k, "owned_k": owned_k}
         return losses[0]
@@ -168,10 +174,15 @@ class CriterionStep:
             k = crit.atts_k(k0)
         f_s = crit.embed_s(self.feat_s)
         f_s = crit.atts_q(f_s)
+        ema_late = os.environ.get("MOMA_B200_EMA_FORK", "early") != "early"       # A/B switch (see _loss_and_backward)
+        if not ema_late:
+            s_ema.wait_stream(s_t)
+            with torch.cuda.stream(s_ema):
+                self.trainer.momentum_update(self.student, self.teacher, opt.alpha)
         # The loss of this step needs q, the local positive keys and the OLD queue -- not the keys enqueued for later
         # steps: only the teacher branch (s_t) joins here, the queue-attention branch (s_u) joins after the backward.
         main.wait_stream(s_t)
-        loss = self._loss_and_backward(f_s, k, all_k, self.feat_s, owned_k=owned, enqueue_stream=s_u, ema_stream=s_ema)
+        loss = self._loss_and_backward(f_s, k, all_k, self.feat_s, owned_k=owned, enqueue_stream=s_u, ema_stream=s_ema if ema_late else None)
         main.wait_stream(s_u)
         main.wait_stream(s_ema)
         return loss

@@ -93,7 +93,8 @@ class TinyTeacher(torch.nn.Module):
         return ([f], logit) if is_feat else logit
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, mode="slices"):
+    os.environ["MOMA_B200_SHUFFLE_BN"] = mode
     sys.path.insert(0, ROOT)
     from argparse import Namespace
     torch.set_num_threads(1)
@@ -121,12 +122,15 @@ def _worker(rank, world, port, ret):
     dist.barrier(); dist.destroy_process_group()
 
 
-def test_shuffle_bn_two_ranks_matches_reference(golden):
+@pytest.mark.parametrize("mode,port", [("slices", 29741), ("gather", 29743)])
+def test_shuffle_bn_two_ranks_matches_reference(golden, mode, port):
     """learning/contrast_trainer.py:90-133: returned k / all_k and the BatchNorm statistics the shuffled
-    batches leave behind equal the unmodified reference's 2-rank run (same seeds -> same permutation)."""
+    batches leave behind equal the unmodified reference's 2-rank run (same seeds -> same permutation), both with the
+    all-to-all of image slices (default: each rank receives only the B images it feeds to the momentum encoder) and
+    with the reference's all-gather of the node's images."""
     g = golden("kat_shufflebn")
     mgr = mp.Manager(); ret = mgr.dict()
-    mp.spawn(_worker, args=(2, 29741, ret), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, ret, mode), nprocs=2, join=True)
     for r in (0, 1):
         for key in ("k", "all_k", "bn_mean", "bn_var"):
             assert np.allclose(ret[r][key], g[f"r{r}_{key}"], rtol=1e-6, atol=1e-7), (r, key)

@@ -340,8 +340,8 @@ def test_fused_nce_equals_three_launch_path_and_oracle(bf16, B, D, K):
     for rep in range(3):
         rows, dq, pim, mx, loss, acc = ops.nce_fused(q16, queue16, q, k, 1 / T, True, 1.0 / B)
         torch.cuda.synchronize()
-        assert torch.allclose(rows, rows0, rtol=2e-6, atol=1e-6), rep
-        assert torch.allclose(dq, dq0, rtol=1e-5, atol=1e-9), rep
+        assert torch.allclose(rows, rows0, rtol=2e-6, atol=2e-6), rep
+        assert rel(npy(dq), npy(dq0)) < 1e-5, rep                      # same partials, different summation grouping
         assert torch.equal(pim, pim0) and torch.allclose(mx, mx0, rtol=1e-6)
         assert abs(loss.item() - loss0.item()) < 2e-6 * abs(loss0.item()) and acc.item() == acc0.item()
     assert int(ops._FUSE_COUNTERS[q.device][0].abs().sum().item()) == 0          # every block back to zero
@@ -353,4 +353,4 @@ def test_fused_nce_equals_three_launch_path_and_oracle(bf16, B, D, K):
     packed = ops.nce_fused_packed(q16, queue16, 1 / T)
     want = ops.nce_merge_packed(stats, Op)
     torch.cuda.synchronize()
-    assert torch.allclose(packed[:, :D + 3], want[:, :D + 3], rtol=1e-5, atol=1e-9)
+    assert rel(npy(packed[:, :D + 3]), npy(want[:, :D + 3])) < 1e-5
