@@ -116,6 +116,8 @@ class Ctx:
         # kernel (an int32 -> int64 sum first materialises a 512 MiB converted copy, i.e. it is a write-flush)
         self.flush_buf = None if args.no_flush else torch.zeros(64 << 20, dtype=torch.float32, device=self.device)
         self.flush_out = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.lockstep = os.environ.get("MOMA_BENCH_LOCKSTEP") == "1"
+        self.last_dist = {}
 
     def flush(self):
         if self.flush_buf is not None:
@@ -144,6 +146,13 @@ class Ctx:
         """Per-step CUDA-event timing on the launching stream (L2 flushed before each step), summed; max over ranks."""
         evs = []
         self.barrier()
+        if self.world > 1:
+            # The barrier releases the ranks' HOSTS up to milliseconds apart; the first exchange of the next step then makes
+            # the early rank's GPU wait for the late one (measured: one 4.3 ms step in 60, i.e. +30 % on the mean).  One
+            # untimed step after the barrier aligns the GPUs on its exchanges; the K timed steps follow back to back in
+            # every rank's stream.
+            self.flush()
+            fn()
         for _ in range(steps):
             self.flush()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -151,8 +160,13 @@ class Ctx:
             fn()
             b.record()
             evs.append((a, b))
+            if self.lockstep:                                  # diagnostic (MOMA_BENCH_LOCKSTEP=1): ranks re-aligned every step
+                self.barrier()
         self.barrier()
-        return self.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs))
+        per = sorted(a.elapsed_time(b) for a, b in evs)
+        self.last_dist = {"min_ms": per[0], "median_ms": per[len(per) // 2], "p90_ms": per[(len(per) * 9) // 10],
+                          "max_ms": per[-1]}                      # this rank's per-step distribution (diagnostic)
+        return self.max_over_ranks(sum(per))
 
     def kernel_us(self, launch, reps=20):
         """One kernel alone, cold L2 (flush first; the flush also hides the launch gap, so e0 -> e1 brackets the
@@ -323,10 +337,12 @@ def measure(ctx: Ctx, name, cfg, steps, strong=False, full=False):
     lib.moma_debug_flops(0, 1); lib.moma_debug_flops(1, 1)
     total_ms = ctx.timed(graphed.replay, steps)
     ms = total_ms / steps
+    dist_free = dict(ctx.last_dist)
     out = {
         "config": name, "workload": cfg["desc"], "scaling": "strong" if strong else "weak", "per_gpu_batch": B,
         "global_batch": n, "feat_dim": D, "queue_K": K, "heads": cfg["H"], "ms_per_step": ms,
         "value": n / (ms * 1e-3), "unit": "samples/s", "steps": steps, "parity_check": parity,
+        "per_step_ms_rank0": dist_free,
         "queue": "replicated" if world == 1 else f"sharded by K over {world} ranks (cyclic), {K // world} rows/rank",
     }
     if world > 1:
@@ -653,7 +669,7 @@ def run_ours(args, rank, world, local_rank):
                    "timed_region": "EMA + projection heads + 3x attention + fused InfoNCE/CE fwd+bwd + enqueue (criterion step, L1)"},
         "parity_check": main["parity_check"],
         "e2e": main["e2e"], "gpu_launches": main["gpu_launches"], "gpu_launches_per_step": main["gpu_launches_per_step"],
-        "eager": main["eager"],
+        "eager": main["eager"], "per_step_ms_rank0": main.get("per_step_ms_rank0"),
         "execution": "whole criterion step (fwd+bwd) captured once as a CUDA graph and replayed; the teacher branch, the "
                      "queue-attention + enqueue branch and the backbone EMA are forked onto side streams inside the capture; "
                      "kernels are chained with programmatic dependent launch",
