@@ -273,6 +273,31 @@ int moma_peer_exchange(const void *src, int64_t src_peer_stride_bytes, int64_t b
                        void *out, moma_stream_t stream);
 
 /* ------------------------------------------------------------------------- *
+ * (f2) optimizer step fused with the momentum-encoder EMA: torch.optim.SGD(momentum, weight_decay; dampening 0, no
+ * Nesterov -- train_student_moma.py:389-392) .step() (helper/loops_moma.py:361) followed by momentum_update
+ * (learning/contrast_trainer.py:207-211, called at the top of the next iteration, loops_moma.py:309) in ONE multi-tensor
+ * pass: 28 B / element instead of 20 + 12 in two passes, one launch instead of ~3 per tensor.  Same rounding sequence as
+ * the two library steps (see csrc/sgd_ema.cu).  Plan protocol as for moma_ema_*: size -> fill a HOST table -> copy to
+ * the device -> moma_sgd_ema_multi every step (first_step != 0: the momentum buffers are created, buf = d).
+ * ------------------------------------------------------------------------- */
+int moma_sgd_ema_plan_size(int n_tensors, const int64_t *numels, int64_t *n_chunks, size_t *table_bytes);
+int moma_sgd_ema_plan_fill(int n_tensors, void *const *param_ptrs, const void *const *grad_ptrs,
+                           void *const *buf_ptrs, void *const *ema_ptrs, const int64_t *numels,
+                           void *host_table, size_t table_bytes);
+int moma_sgd_ema_multi(const void *dev_table, int64_t n_chunks, float lr, float momentum, float weight_decay,
+                       int first_step, float m, float one_minus_m, moma_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * (f3) the consumers either side of the MoMA loss on the [B, n_cls] student / teacher logits, one launch:
+ * classification CE (train_student_moma.py:294, helper/loops_moma.py:278), Hinton KD
+ * DistillKL(T) (distiller_zoo/KD.py:7-17, loops_moma.py:279) and top-1 accuracy (helper/util.py:71-85, :350),
+ * as three device scalars out3 = (loss_cls, loss_div, acc_pct) plus the gradients of the two losses with respect to
+ * logit_s ([B, n_cls] each), so the autograd backward is a scalar multiply-add.  labels: int64 [B].  n_cls <= 1024.
+ * ------------------------------------------------------------------------- */
+int moma_cls_kd(const float *logit_s, const float *logit_t, const int64_t *labels, int64_t B, int64_t n_cls,
+                float T, float *out3, float *grad_cls, float *grad_div, moma_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
  * debug / test hooks (not used by the product path)
  * moma_debug_nce_tc: the tcgen05 partial kernel with an optional dump of the raw
  *   score tile S = Q . Tile^T of the first queue tile of split 0:

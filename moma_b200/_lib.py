@@ -25,6 +25,10 @@ SIGNATURES = {
     "moma_ema_plan_size": (c_int, [c_int, POINTER(_i64), POINTER(_i64), POINTER(c_size_t)]),
     "moma_ema_plan_fill": (c_int, [c_int, POINTER(_vp), POINTER(_vp), POINTER(_i64), _vp, c_size_t]),
     "moma_ema_multi": (c_int, [_vp, _i64, c_float, c_float, _vp]),
+    "moma_sgd_ema_plan_size": (c_int, [c_int, POINTER(_i64), POINTER(_i64), POINTER(c_size_t)]),
+    "moma_sgd_ema_plan_fill": (c_int, [c_int, POINTER(_vp), POINTER(_vp), POINTER(_vp), POINTER(_vp), POINTER(_i64), _vp,
+                                       c_size_t]),
+    "moma_sgd_ema_multi": (c_int, [_vp, _i64, c_float, c_float, c_float, c_int, c_float, c_float, _vp]),
     "moma_l2norm_fwd": (c_int, [_vp, _vp, _i64, _i64, c_float, _vp]),
     "moma_l2norm_bwd": (c_int, [_vp, _vp, _vp, _i64, _i64, c_float, _vp]),
     "moma_enqueue": (c_int, [_vp, _i64, _i64, _vp, _vp, _i64, _i64, _vp, c_int, c_int, c_int, c_float, _vp]),
@@ -33,6 +37,7 @@ SIGNATURES = {
     "moma_pointer_advance": (c_int, [_vp, _i64, _i64, _vp]),
     "moma_cast_bf16": (c_int, [_vp, _vp, _i64, _vp]),
     "moma_scale_by_scalar": (c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "moma_cls_kd": (c_int, [_vp, _vp, _vp, _i64, _i64, c_float, _vp, _vp, _vp, _vp]),
     "moma_nce_num_splits": (c_int, [_i64, _i64, _i64, c_int]),
     "moma_nce_partial": (c_int, [_vp, _vp, _i64, _i64, _i64, c_float, c_int, c_int, _vp, _vp, _vp, _vp, _vp]),
     "moma_nce_combine": (c_int, [_vp, _vp, _vp, _vp, c_int, _vp, _vp, _i64, _i64, c_float, c_int, c_float,

@@ -633,3 +633,108 @@ def linear(x, weight, bias=None, relu: bool = False, key=None):
     if x.dim() != 2 or weight.dim() != 2 or x.shape[1] != weight.shape[1]:
         raise RuntimeError(f"moma_b200.linear: bad shapes x {tuple(x.shape)} weight {tuple(weight.shape)}")
     return _Linear.apply(x, weight, bias, bool(relu), key if key is not None else "linear")
+
+
+# -------------------------------------------------------------------------- classification CE + KD + top-1
+class _ClsKd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logit_s, logit_t, labels, T):
+        ls, lt = _f32c(logit_s), _f32c(logit_t.detach())
+        B, C = ls.shape
+        out = torch.empty(3, dtype=torch.float32, device=ls.device)
+        g_cls, g_div = torch.empty_like(ls), torch.empty_like(ls)
+        check(_lib.load().moma_cls_kd(_p(ls), _p(lt), _p(labels.contiguous()), B, C, float(T), _p(out), _p(g_cls), _p(g_div),
+                                      _stream()))
+        ctx.save_for_backward(g_cls, g_div)
+        ctx.set_materialize_grads(False)
+        acc = out[2:3]
+        ctx.mark_non_differentiable(acc)
+        return out[0], out[1], acc
+
+    @staticmethod
+    def backward(ctx, g1, g2, *unused):
+        g_cls, g_div = ctx.saved_tensors
+        grad = None
+        if g1 is not None:
+            grad = g_cls * g1
+        if g2 is not None:
+            grad = g_div * g2 if grad is None else torch.addcmul(grad, g_div, g2)
+        return grad, None, None, None
+
+
+def cls_kd_losses(logit_s, logit_t, labels, T: float):
+    """(loss_cls, loss_div, acc_top1 [1]) = (CrossEntropyLoss()(logit_s, labels), DistillKL(T)(logit_s, logit_t),
+    accuracy(logit_s, labels)[0]) from one kernel launch; differentiable with respect to logit_s
+    (helper/loops_moma.py:278-279,350 / distiller_zoo/KD.py:7-17 / helper/util.py:71-85)."""
+    _need_cuda(logit_s, logit_t, labels)
+    if logit_s.dim() != 2 or logit_s.shape != logit_t.shape or labels.dtype != torch.int64 or labels.shape[0] != logit_s.shape[0]:
+        raise RuntimeError("moma_b200.cls_kd_losses: expects logit_s, logit_t [B, n_cls] and int64 labels [B]")
+    return _ClsKd.apply(logit_s, logit_t, labels, float(T))
+
+
+# -------------------------------------------------------------------------- SGD + EMA in one pass (SURVEY 8f-2)
+class FusedSgdEma:
+    """``torch.optim.SGD(params, lr, momentum, weight_decay).step()`` followed by
+    ``ContrastTrainer.momentum_update(model, model_ema, m)`` as ONE multi-tensor launch
+    (train_student_moma.py:389-392, helper/loops_moma.py:361 -> :309; same rounding sequence as the two library steps).
+
+        opt = FusedSgdEma(model.parameters(), model_ema.parameters(), lr=0.05, momentum=0.9, weight_decay=5e-4, m=0.999)
+        loss.backward(); opt.step()            # instead of optimizer.step() ... trainer.momentum_update(...)
+
+    Parameters without a gradient are skipped by the SGD part of torch; here every parameter must have a ``.grad``.
+    The pointer table is rebuilt only when a gradient tensor was re-allocated (``zero_grad(set_to_none=True)``)."""
+
+    def __init__(self, params, ema_params, lr, momentum=0.0, weight_decay=0.0, m=0.999):
+        self.params, self.emas = list(params), list(ema_params)
+        if len(self.params) != len(self.emas):
+            raise RuntimeError("FusedSgdEma: parameter lists differ in length")
+        for p, e in zip(self.params, self.emas):
+            if p.shape != e.shape:
+                raise RuntimeError(f"The size of tensor a {tuple(e.shape)} must match the size of tensor b {tuple(p.shape)}")
+            if p.dtype != torch.float32 or e.dtype != torch.float32 or not (p.is_contiguous() and e.is_contiguous()):
+                raise RuntimeError("FusedSgdEma: contiguous float32 parameters only")
+        _need_cuda(*self.params, *self.emas)
+        self.lr, self.momentum, self.weight_decay, self.m = float(lr), float(momentum), float(weight_decay), float(m)
+        self.bufs = [torch.zeros_like(p) for p in self.params]
+        self.steps = 0
+        self._key, self._table, self._n_chunks = None, None, 0
+
+    def _plan(self):
+        grads = []
+        for p in self.params:
+            if p.grad is None:
+                raise RuntimeError("FusedSgdEma.step: a parameter has no gradient")
+            g = p.grad
+            if g.dtype != torch.float32 or not g.is_contiguous():
+                raise RuntimeError("FusedSgdEma.step: contiguous float32 gradients only")
+            grads.append(g)
+        key = tuple(g.data_ptr() for g in grads)
+        if key == self._key:
+            return
+        lib = _lib.load()
+        n = len(self.params)
+        numels = (ctypes.c_int64 * n)(*[int(p.numel()) for p in self.params])
+        n_chunks, nbytes = ctypes.c_int64(0), ctypes.c_size_t(0)
+        check(lib.moma_sgd_ema_plan_size(n, numels, ctypes.byref(n_chunks), ctypes.byref(nbytes)))
+        host = torch.empty(max(nbytes.value, 64), dtype=torch.uint8).pin_memory()
+        arr = lambda ts: (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts])
+        check(lib.moma_sgd_ema_plan_fill(n, arr([p.detach() for p in self.params]), arr(grads), arr(self.bufs),
+                                         arr([e.detach() for e in self.emas]), numels, host.data_ptr(), host.numel()))
+        self._host = host
+        self._table = host.to(self.params[0].device, non_blocking=False)
+        self._n_chunks, self._key = n_chunks.value, key
+
+    @torch.no_grad()
+    def step(self):
+        self._plan()
+        check(_lib.load().moma_sgd_ema_multi(_p(self._table), self._n_chunks, self.lr, self.momentum, self.weight_decay,
+                                             int(self.steps == 0), self.m, float(1 - self.m), _stream()))
+        self.steps += 1
+
+    def zero_grad(self, set_to_none: bool = False):
+        for p in self.params:
+            if p.grad is not None:
+                if set_to_none:
+                    p.grad = None
+                else:
+                    p.grad.zero_()

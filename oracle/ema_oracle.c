@@ -29,3 +29,24 @@ void moma_oracle_enqueue_ids(int64_t *out, int64_t n, int64_t index, int64_t K)
     for (int64_t j = 0; j < n; ++j)
         out[j] = (j + index) % K;
 }
+
+/* moma_oracle_sgd_ema_f32 restates torch.optim.SGD(momentum, weight_decay; dampening 0, no Nesterov).step()
+ * (train_student_moma.py:389-392, helper/loops_moma.py:361) followed by momentum_update
+ * (learning/contrast_trainer.py:207-211) with the rounding sequence of the ATen kernels:
+ *     d   = fl(fma(wd, p, g))               -- grad.add(param, alpha=weight_decay)
+ *     buf = first ? d : fl(fl(buf * mu) + d) -- buf.mul_(momentum).add_(d, alpha=1)
+ *     p   = fl(fma(-lr, buf, p))            -- param.add_(buf, alpha=-lr)
+ *     ema = fl(fma(alpha, p, fl(ema * m)))
+ * Pinned against torch.optim.SGD + the reference's momentum_update on CPU by tests/test_oracle_round2.py. */
+void moma_oracle_sgd_ema_f32(float *p, const float *g, float *buf, float *ema, int64_t n, float lr, float mu, float wd,
+                             int first, float m, float alpha)
+{
+    for (int64_t i = 0; i < n; ++i) {
+        float d = fmaf(wd, p[i], g[i]);
+        float b = first ? d : (buf[i] * mu) + d;
+        buf[i] = b;
+        p[i] = fmaf(-lr, b, p[i]);
+        float t = ema[i] * m;
+        ema[i] = fmaf(alpha, p[i], t);
+    }
+}

@@ -386,9 +386,31 @@ def kat_shufflebn():
     save("kat_shufflebn", **out)
 
 
+# ------------------------------------- classification CE + DistillKL + accuracy
+def kat_kd():
+    """helper/loops_moma.py:278-279,350: CrossEntropyLoss, distiller_zoo.DistillKL(4), helper.util.accuracy on [B, n_cls]."""
+    from distiller_zoo import DistillKL
+    from helper.util import accuracy as acc_fn
+    out = {}
+    for tag, (B, C, T) in {"a": (16, 4, 4.0), "b": (37, 8, 2.0), "c": (5, 100, 1.0)}.items():
+        torch.manual_seed(900 + B)
+        ys = (torch.randn(B, C) * 3).requires_grad_()
+        yt = torch.randn(B, C) * 3
+        lab = torch.randint(0, C, (B,))
+        l_cls = nn.CrossEntropyLoss()(ys, lab)
+        l_div = DistillKL(T)(ys, yt)
+        acc = acc_fn(ys, lab, topk=(1,))[0]
+        g_cls, = torch.autograd.grad(l_cls, ys, retain_graph=True)
+        g_div, = torch.autograd.grad(l_div, ys)
+        out.update({f"{tag}_ys": npy(ys), f"{tag}_yt": npy(yt), f"{tag}_lab": npy(lab), f"{tag}_T": np.float32(T),
+                    f"{tag}_cls": np.float32(l_cls.item()), f"{tag}_div": np.float32(l_div.item()), f"{tag}_acc": npy(acc),
+                    f"{tag}_gcls": npy(g_cls), f"{tag}_gdiv": npy(g_div)})
+    save("kat_kd", **out)
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     for fn in (kat_moco, kat_pointer, kat_attention, kat_normalize, kat_ema, criterion_step, kat_dual, kat_gloo,
-               kat_mocoatt, kat_heads, kat_shufflebn):
+               kat_mocoatt, kat_heads, kat_shufflebn, kat_kd):
         if not only or fn.__name__ in only:
             fn()

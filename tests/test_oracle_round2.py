@@ -155,3 +155,41 @@ def test_criterion_step_oracle_matches_reference_run(golden):
         assert rel(out["f_s"], g[f"st{st}_f_s"]) < 2e-6 and rel(out["k"], g[f"st{st}_k2"]) < 2e-6
         sd = {k[len(f"st{st}_sd_"):]: g[k] for k in g.files if k.startswith(f"st{st}_sd_")}      # after the SGD step
         mem = g[f"st{st}_mem"]
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_cls_kd_oracle(golden, tag):
+    """CrossEntropyLoss / DistillKL / their gradients restated (helper/loops_moma.py:278-279, distiller_zoo/KD.py:7-17)
+    against the unmodified reference modules."""
+    g = golden("kat_kd")
+    ys, yt, lab, T = g[f"{tag}_ys"].astype(np.float64), g[f"{tag}_yt"].astype(np.float64), g[f"{tag}_lab"], float(g[f"{tag}_T"])
+    assert abs(O.cross_entropy(ys, lab) - float(g[f"{tag}_cls"])) < 2e-6 * abs(float(g[f"{tag}_cls"]))
+    assert abs(O.distill_kl(ys, yt, T) - float(g[f"{tag}_div"])) < 2e-6 * abs(float(g[f"{tag}_div"]))
+    gc, gd = O.cls_kd_grads(ys, yt, lab, T)
+    assert rel(gc, g[f"{tag}_gcls"]) < 2e-6 and rel(gd, g[f"{tag}_gdiv"]) < 2e-6
+    assert O.accuracy_top1(ys, lab) == pytest.approx(float(g[f"{tag}_acc"][0]))
+
+
+def test_sgd_ema_oracle_matches_torch_sgd_then_momentum_update():
+    """The C restatement of SGD(momentum, weight_decay).step() + momentum_update against torch.optim.SGD on CPU and the
+    reference's own momentum_update formula, 3 steps (the first one creates the momentum buffers)."""
+    torch.manual_seed(5)
+    shapes = [(7,), (33, 17), (4097,), (64, 3, 3, 3)]
+    ps = [torch.nn.Parameter(torch.randn(*s)) for s in shapes]
+    es = [torch.randn(*s) for s in shapes]
+    opt = torch.optim.SGD(ps, lr=0.05, momentum=0.9, weight_decay=5e-4)
+    P = [p.detach().numpy().copy() for p in ps]
+    E = [e.numpy().copy() for e in es]
+    Bf = [np.zeros_like(p) for p in P]
+    for step in range(3):
+        grads = [torch.randn(*s) for s in shapes]
+        for p, g in zip(ps, grads):
+            p.grad = g.clone()
+        opt.step()
+        for p1, p2 in zip(ps, es):                                   # learning/contrast_trainer.py:209-211
+            p2.data.mul_(0.999).add_(p1.detach().data, alpha=(1 - 0.999))
+        O.sgd_ema_step(P, [g.numpy().copy() for g in grads], Bf, E, 0.05, 0.9, 5e-4, step == 0, 0.999)
+        for a, b in zip(P, ps):
+            assert np.array_equal(a, b.detach().numpy()), step
+        for a, b in zip(E, es):
+            assert np.array_equal(a, b.numpy()), step

@@ -354,3 +354,54 @@ def test_fused_nce_equals_three_launch_path_and_oracle(bf16, B, D, K):
     want = ops.nce_merge_packed(stats, Op)
     torch.cuda.synchronize()
     assert rel(npy(packed[:, :D + 3]), npy(want[:, :D + 3])) < 1e-5
+
+
+# ------------------------------------------------------------------ classification CE + KD + top-1 in one launch (8f-3)
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_cls_kd_fused_golden(golden, tag):
+    """ops.cls_kd_losses == (CrossEntropyLoss, DistillKL(T), accuracy) of the reference on its own inputs, values and
+    gradients (through an arbitrary weighting cls * l_cls + div * l_div as at helper/loops_moma.py:345)."""
+    from moma_b200 import ops
+    g = golden("kat_kd")
+    ys = cu(g[f"{tag}_ys"]).requires_grad_()
+    yt, lab, T = cu(g[f"{tag}_yt"]), cu(g[f"{tag}_lab"]), float(g[f"{tag}_T"])
+    l_cls, l_div, acc = ops.cls_kd_losses(ys, yt, lab, T)
+    assert abs(l_cls.item() - float(g[f"{tag}_cls"])) < 2e-6 * abs(float(g[f"{tag}_cls"]))
+    assert abs(l_div.item() - float(g[f"{tag}_div"])) < 5e-6 * abs(float(g[f"{tag}_div"]))
+    assert acc.item() == pytest.approx(float(g[f"{tag}_acc"][0]))
+    (0.7 * l_cls + 1.3 * l_div).backward()
+    want = 0.7 * g[f"{tag}_gcls"] + 1.3 * g[f"{tag}_gdiv"]
+    assert rel(npy(ys.grad), want) < TOL
+
+
+# ------------------------------------------------------------------ SGD + EMA in one pass (8f-2)
+def test_fused_sgd_ema_bit_exact():
+    """ops.FusedSgdEma.step() == torch.optim.SGD(momentum 0.9, wd 5e-4).step() followed by momentum_update, bit for bit,
+    against torch's CUDA kernels and against the C oracle; odd sizes, an unaligned view, re-allocated gradients."""
+    from moma_b200 import ContrastTrainer, ops
+    torch.manual_seed(9)
+    shapes = [(7,), (33, 17), (4097,), (64, 3, 3, 3), (100003,), (512, 512)]
+    base = [torch.randn(*s) for s in shapes]
+    ema0 = [torch.randn(*s) for s in shapes]
+    pa = torch.nn.ParameterList([torch.nn.Parameter(b.clone()) for b in base]).cuda()       # fused
+    ea = torch.nn.ParameterList([torch.nn.Parameter(e.clone()) for e in ema0]).cuda()
+    pb = torch.nn.ParameterList([torch.nn.Parameter(b.clone()) for b in base]).cuda()       # torch SGD + momentum_update
+    eb = torch.nn.ParameterList([torch.nn.Parameter(e.clone()) for e in ema0]).cuda()
+    fused = ops.FusedSgdEma(pa, ea, lr=0.05, momentum=0.9, weight_decay=5e-4, m=0.999)
+    opt = torch.optim.SGD(pb, lr=0.05, momentum=0.9, weight_decay=5e-4)
+    P = [b.numpy().copy() for b in base]; E = [e.numpy().copy() for e in ema0]; Bf = [np.zeros_like(p) for p in P]
+    for step in range(4):
+        grads = [torch.randn(*s) for s in shapes]
+        for p, q, g in zip(pa, pb, grads):
+            p.grad = g.clone().cuda()                     # new tensors every step: the pointer table must follow
+            q.grad = g.clone().cuda()
+        fused.step()
+        opt.step()
+        ContrastTrainer.momentum_update(pb, eb, 0.999)
+        O.sgd_ema_step(P, [g.numpy().copy() for g in grads], Bf, E, 0.05, 0.9, 5e-4, step == 0, 0.999)
+        for i in range(len(shapes)):
+            assert torch.equal(pa[i], pb[i]), (step, i)
+            assert torch.equal(ea[i], eb[i]), (step, i)
+            assert np.array_equal(npy(pa[i]), P[i]) and np.array_equal(npy(ea[i]), E[i]), (step, i)
+    with pytest.raises(RuntimeError):
+        ops.FusedSgdEma([torch.zeros(3, 4, device="cuda")], [torch.zeros(4, 3, device="cuda")], lr=0.1)
