@@ -329,7 +329,9 @@ int gemm_splits(int M, int N, int K) {
     const int ktiles = (K + kTK - 1) / kTK;
     // CTAs aimed at per SM (MOMA_B200_GEMM_OVERSUB, read once; default 2: measured -3 % on the C2 step against 1, 3 gives nothing more)
     static const int oversub = [] { const char* e = getenv("MOMA_B200_GEMM_OVERSUB"); int v = e ? atoi(e) : 2; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
-    const int target = sm_count() * oversub;
+    // deep contractions (K >= 1024: the teacher head's second layer, 2048 -> D) have few output tiles and many slabs:
+    // twice the CTAs again, the extra fix-up reads are L2 hits
+    const int target = sm_count() * oversub * (ktiles >= 32 ? 2 : 1);
     if (tiles * 5 >= target * 4) return 1;                     // >= 0.8 wave already
     int s = target / tiles;
     s = s < ktiles / 4 ? s : ktiles / 4;                       // >= 4 K-slabs per split: the fix-up costs two L2 round trips

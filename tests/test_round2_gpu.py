@@ -345,6 +345,22 @@ def test_fused_nce_equals_three_launch_path_and_oracle(bf16, B, D, K):
         assert torch.equal(pim, pim0) and torch.allclose(mx, mx0, rtol=1e-6)
         assert abs(loss.item() - loss0.item()) < 2e-6 * abs(loss0.item()) and acc.item() == acc0.item()
     assert int(ops._FUSE_COUNTERS[q.device][0].abs().sum().item()) == 0          # every block back to zero
+    # and through the module API with the one-launch path switched on
+    import os
+    from moma_b200 import MoCo
+    os.environ["MOMA_B200_NCE_FUSED"] = "1"
+    try:
+        m = MoCo(D, K, T).cuda()
+        with torch.no_grad():
+            m.memory.copy_(queue)
+        m.invalidate_shadows()
+        qq = q.clone().requires_grad_()
+        logits, labels = m(qq, k)
+        lm = torch.nn.functional.cross_entropy(logits, labels)
+        lm.backward()
+        assert abs(lm.item() - loss0.item()) < 2e-6 * abs(loss0.item()) and rel(npy(qq.grad), npy(dq0)) < 1e-5
+    finally:
+        os.environ["MOMA_B200_NCE_FUSED"] = "0"
     r_ = lambda t: O.round_bf16(npy(t)).astype(np.float64)
     loss_o, rows_o, dq_o, pim_o = O.nce_loss_and_grad(r_(q), r_(k), r_(queue), T)
     assert abs(loss.item() - loss_o) < 1e-3 * abs(loss_o) and rel(npy(dq), dq_o) < 1e-3
