@@ -23,6 +23,9 @@ from . import ops
 from .lazy_logits import LazyLogits
 
 
+_PEER_GATHER_MAX_BYTES = int(os.environ.get("MOMA_B200_PEER_GATHER_MAX_BYTES", 1 << 20))
+
+
 class AverageMeter(object):
     """Computes and stores the average and current value (reference learning/util.py:7-22)"""
 
@@ -171,7 +174,12 @@ class ContrastTrainer(BaseTrainer):
         """all_gather + cat(dim=0) -> [W*B, D]  (reference :83-88)"""
         world = dist.get_world_size()
         x = x.contiguous()
-        if x.is_cuda and x.dtype == torch.float32 and (x.numel() * 4) % 16 == 0:
+        # The peer-memory kernel is a LATENCY tool: every payload word travels with an in-band tag (2x the bytes) and the
+        # receiver polls cells.  Past ~1 MiB gathered that costs more than it saves and crowds the NVLink queues of the
+        # small exchanges on the step's critical path (measured at 8 GPUs: a 12.6 MB tagged gather delayed the 131 KB
+        # query gather from 8 to 70 us), so large gathers take the NCCL collective (NVLS / ring over NVSwitch).
+        small = world * x.numel() * x.element_size() <= _PEER_GATHER_MAX_BYTES
+        if small and x.is_cuda and x.dtype == torch.float32 and (x.numel() * 4) % 16 == 0:
             from .peer import CH_KEYS, PeerExchange
             peer = PeerExchange.create(None, x.device, 2 * world * x.numel() * 4)
             if peer is not None:                       # one NVLink push/flag/wait kernel instead of the collective

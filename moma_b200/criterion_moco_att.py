@@ -17,6 +17,7 @@ from torch import nn
 from . import ops
 
 eps = 1e-7
+_GATHER_PROJECTIONS_MAX_BYTES = int(os.environ.get("MOMA_B200_GATHER_PROJECTIONS_MAX_BYTES", 2 << 20))
 
 
 class Normalize(nn.Module):
@@ -141,12 +142,20 @@ class Attention(nn.Module):
 
 
     def forward_rows_gathered(self, x_local, gather, q_start, q_stride, q_count):
-        """``forward_rows`` over the concatenation of every rank's ``x_local`` without any rank projecting all of
-        it: each rank projects its own rows (qkv Linear), the projections are all-gathered (``gather``: [B, 3C] ->
-        [W * B, 3C], e.g. ContrastTrainer._global_gather) and the attention runs for the requested rows.  No autograd."""
+        """``forward_rows`` over the concatenation of every rank's ``x_local`` (``gather``: [B, .] -> [W * B, .], e.g.
+        ContrastTrainer._global_gather).  No autograd.  Two schedules, chosen by the bytes that would cross NVLink:
+          * few ranks: every rank projects only its own rows (qkv Linear) and the PROJECTIONS are all-gathered
+            (3C floats per token) -- no rank projects a token twice;
+          * many ranks: the raw tokens are all-gathered (C floats per token, the reference's key gather,
+            learning/contrast_trainer.py:124) and projected locally -- 3x fewer bytes on the wire for one extra small GEMM
+            (at 8 x 512 tokens: 2.1 MB instead of 6.3 MB gathered per rank)."""
         with torch.no_grad():
             if not self._fusable(x_local):
                 return self._composed(gather(x_local))[q_start::q_stride][:q_count]
+            n_tokens = q_stride * q_count if q_stride > 1 else x_local.shape[0]
+            if n_tokens * 3 * x_local.shape[1] * 4 > _GATHER_PROJECTIONS_MAX_BYTES:
+                return ops.attention_rows(gather(x_local), self.qkv.weight, self.qkv.bias, self.proj.weight, self.proj.bias,
+                                          self.num_heads, q_start, q_stride, q_count)
             qkv_local = ops.linear(x_local, self.qkv.weight, self.qkv.bias, key="rows_gathered")
             return ops.attention_rows_from_qkv(gather(qkv_local), self.proj.weight, self.proj.bias, self.num_heads,
                                                q_start, q_stride, q_count)

@@ -62,11 +62,11 @@ __device__ __forceinline__ float quad_sum(float v) {
 }
 
 // 64 rows x HD floats, global (row stride `rs` floats) -> shared [64][HD + 4]; rows >= n_valid are zero-filled
-template <int HD>
+template <int HD, int THREADS = kThreads>
 __device__ __forceinline__ void load_tile(float* dst, const float* __restrict__ src, int64_t rs, int row0, int n_valid) {
     constexpr int LD = HD + 4, V = HD / 4;
 #pragma unroll
-    for (int i = threadIdx.x; i < kTile * V; i += kThreads) {
+    for (int i = threadIdx.x; i < kTile * V; i += THREADS) {
         const int r = i / V, v = i - r * V;
         const bool ok = row0 + r < n_valid;
         cp_async16(dst + r * LD + 4 * v, ok ? src + (int64_t)(row0 + r) * rs + 4 * v : src, ok);
@@ -109,16 +109,17 @@ __device__ __forceinline__ void load_a_rows(const float* __restrict__ p_lo, cons
 }
 
 // ---------------------------------------------------------------------------------------------------- forward
-template <int HD>
-__global__ void __launch_bounds__(kThreads)
+// WARPS: 16 query rows each; 4 for the usual grids, 2 or 1 when rows x heads would leave most SMs idle
+template <int HD, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS)
 attn_fwd_tc_kernel(const float* __restrict__ qkv, int N, int C, float scale, float* __restrict__ o, float* __restrict__ lse,
                    int q_start, int q_stride, int NQ) {
     pdl_wait();
     pdl_launch_dependents();
-    constexpr int LD = HD + 4, KS = HD / 8, NT = HD / 8;
+    constexpr int LD = HD + 4, KS = HD / 8, NT = HD / 8, THREADS = 32 * WARPS;
     extern __shared__ __align__(16) float smem[];
     constexpr int STAGE = 2 * kTile * LD;                       // K tile then V tile
-    const int h = blockIdx.y, q0 = blockIdx.x * kRows;
+    const int h = blockIdx.y, q0 = blockIdx.x * (16 * WARPS);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int r_lo = q0 + warp * 16 + g, r_hi = r_lo + 8;
     const int64_t ld3 = 3ll * C;
@@ -135,16 +136,16 @@ attn_fwd_tc_kernel(const float* __restrict__ qkv, int N, int C, float scale, flo
     float m_lo = -CUDART_INF_F, m_hi = -CUDART_INF_F, l_lo = 0.f, l_hi = 0.f;
 
     const int ntiles = (N + kTile - 1) / kTile;
-    load_tile<HD>(smem, kbase, ld3, 0, N);
-    load_tile<HD>(smem + kTile * LD, vbase, ld3, 0, N);
+    load_tile<HD, THREADS>(smem, kbase, ld3, 0, N);
+    load_tile<HD, THREADS>(smem + kTile * LD, vbase, ld3, 0, N);
     cp_async_commit();
     for (int kt = 0; kt < ntiles; ++kt) {
         cp_async_wait<0>();
         __syncthreads();                               // tile kt visible; everyone is done with tile kt - 1
         if (kt + 1 < ntiles) {
             float* nxt = smem + ((kt + 1) & 1) * STAGE;
-            load_tile<HD>(nxt, kbase, ld3, (kt + 1) * kTile, N);
-            load_tile<HD>(nxt + kTile * LD, vbase, ld3, (kt + 1) * kTile, N);
+            load_tile<HD, THREADS>(nxt, kbase, ld3, (kt + 1) * kTile, N);
+            load_tile<HD, THREADS>(nxt + kTile * LD, vbase, ld3, (kt + 1) * kTile, N);
             cp_async_commit();
         }
         const float* K = smem + (kt & 1) * STAGE;
@@ -426,12 +427,21 @@ attn_bwd_dkv_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ 
 template <int HD> constexpr size_t kv_smem() { return (size_t)4 * kTile * (HD + 4) * sizeof(float); }
 template <int HD> constexpr size_t dkv_smem() { return (size_t)2 * (2 * kTile * (HD + 4) + 2 * kTile) * sizeof(float); }
 
+template <int HD, int WARPS>
+static void fwd_w(const float* qkv, int N, int C, int H, float scale, float* o, float* lse, cudaStream_t st, int q_start,
+                  int q_stride, int NQ) {
+    ensure_dyn_smem(reinterpret_cast<const void*>(attn_fwd_tc_kernel<HD, WARPS>), (int)kv_smem<HD>());
+    launch_pdl(attn_fwd_tc_kernel<HD, WARPS>, dim3((NQ + 16 * WARPS - 1) / (16 * WARPS), H), dim3(32 * WARPS), kv_smem<HD>(), st, qkv,
+               N, C, scale, o, lse, q_start, q_stride, NQ);
+}
 template <int HD>
 static void fwd(const float* qkv, int N, int C, int H, float scale, float* o, float* lse, cudaStream_t st, int q_start,
                 int q_stride, int NQ) {
-    ensure_dyn_smem(reinterpret_cast<const void*>(attn_fwd_tc_kernel<HD>), (int)kv_smem<HD>());
-    launch_pdl(attn_fwd_tc_kernel<HD>, dim3((NQ + kRows - 1) / kRows, H), dim3(kThreads), kv_smem<HD>(), st, qkv, N, C, scale, o, lse,
-               q_start, q_stride, NQ);
+    // the largest CTA (most K/V-tile reuse) that still gives about one CTA per SM
+    const int target = sm_count() * 3 / 4;
+    if (((NQ + 63) / 64) * H >= target) fwd_w<HD, 4>(qkv, N, C, H, scale, o, lse, st, q_start, q_stride, NQ);
+    else if (((NQ + 31) / 32) * H >= target) fwd_w<HD, 2>(qkv, N, C, H, scale, o, lse, st, q_start, q_stride, NQ);
+    else fwd_w<HD, 1>(qkv, N, C, H, scale, o, lse, st, q_start, q_stride, NQ);
 }
 template <int HD>
 static void bwd(const float* qkv, const float* dO, const float* lse, const float* delta, int N, int C, int H, float scale,

@@ -270,6 +270,10 @@ def _fuse_counters(device) -> torch.Tensor:
     return ent[0][ent[1]]
 
 
+def nce_fused_supported(B: int, D: int, K_local: int) -> bool:
+    return os.environ.get("MOMA_B200_NCE_FUSED", "") != "never" and bool(_lib.load().moma_nce_fused_supported(B, D, K_local))
+
+
 def nce_fused_enabled(B: int, D: int, K_local: int) -> bool:
     """MOMA_B200_NCE_FUSED=1 runs the whole InfoNCE pass as ONE launch (tcgen05 kernel with the in-kernel combine).
     Default off: measured on the B200 the step takes the same time either way (C2 0.171 / 0.171 ms, C3 0.214 / 0.212 ms

@@ -180,7 +180,11 @@ class ShardedMoCo(BaseMoCo):
                 dist.all_gather_into_tensor(all_q, q_op.contiguous(), group=group)
             # 2. local pass over this rank's K / W rows for all n queries, then fold the splits
             queue = shadow if use_bf16 else memory_shard
-            if use_bf16 and ops.nce_fused_enabled(all_q.shape[0], D, queue.shape[0]):
+            # few K-splits per query tile (many ranks -> many query tiles): the merge of the splits runs in the tail of the
+            # tensor-core kernel (one launch, a handful of L2 round trips) instead of a 4096-CTA merge kernel
+            few_splits = use_bf16 and ops.nce_num_splits(all_q.shape[0], D, queue.shape[0], ops.BF16) <= 8
+            if use_bf16 and (few_splits or ops.nce_fused_enabled(all_q.shape[0], D, queue.shape[0])) \
+                    and ops.nce_fused_supported(all_q.shape[0], D, queue.shape[0]):
                 packed = ops.nce_fused_packed(all_q, queue, inv_T)       # pass + merge of the K-splits in ONE launch
             else:
                 stats, Opart = ops.nce_partial(all_q, queue, inv_T, dtype)
