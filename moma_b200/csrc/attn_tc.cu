@@ -437,10 +437,13 @@ static void fwd_w(const float* qkv, int N, int C, int H, float scale, float* o, 
 template <int HD>
 static void fwd(const float* qkv, int N, int C, int H, float scale, float* o, float* lse, cudaStream_t st, int q_start,
                 int q_stride, int NQ) {
-    // the largest CTA (most K/V-tile reuse) that still gives about one CTA per SM
-    const int target = sm_count() * 3 / 4;
-    if (((NQ + 63) / 64) * H >= target) fwd_w<HD, 4>(qkv, N, C, H, scale, o, lse, st, q_start, q_stride, NQ);
-    else if (((NQ + 31) / 32) * H >= target) fwd_w<HD, 2>(qkv, N, C, H, scale, o, lse, st, q_start, q_stride, NQ);
+    // 4 warps (64 query rows) per CTA.  Smaller CTAs (2 / 1 warps, more CTAs when rows x heads < SMs) were measured at
+    // 8 GPUs on the owned-rows attention (512 rows x 4096 keys): 128 two-warp CTAs took 219 us where 64 four-warp CTAs take
+    // 77 us next to the rest of the step -- every CTA streams all K/V tiles, and fewer, fatter CTAs disturb fewer SMs.
+    // MOMA_B200_ATTN_WARPS=2|1 selects them (A/B switch, read once).
+    static const int warps = [] { const char* e = getenv("MOMA_B200_ATTN_WARPS"); int v = e ? atoi(e) : 4; return (v == 1 || v == 2) ? v : 4; }();
+    if (warps == 4) fwd_w<HD, 4>(qkv, N, C, H, scale, o, lse, st, q_start, q_stride, NQ);
+    else if (warps == 2) fwd_w<HD, 2>(qkv, N, C, H, scale, o, lse, st, q_start, q_stride, NQ);
     else fwd_w<HD, 1>(qkv, N, C, H, scale, o, lse, st, q_start, q_stride, NQ);
 }
 template <int HD>
