@@ -23,7 +23,7 @@ from . import ops
 from .lazy_logits import LazyLogits
 
 
-_PEER_GATHER_MAX_BYTES = int(os.environ.get("MOMA_B200_PEER_GATHER_MAX_BYTES", 1 << 20))
+_PEER_GATHER_MAX_BYTES = int(os.environ.get("MOMA_B200_PEER_GATHER_MAX_BYTES", 64 << 20))
 
 
 class AverageMeter(object):
@@ -174,10 +174,11 @@ class ContrastTrainer(BaseTrainer):
         """all_gather + cat(dim=0) -> [W*B, D]  (reference :83-88)"""
         world = dist.get_world_size()
         x = x.contiguous()
-        # The peer-memory kernel is a LATENCY tool: every payload word travels with an in-band tag (2x the bytes) and the
-        # receiver polls cells.  Past ~1 MiB gathered that costs more than it saves and crowds the NVLink queues of the
-        # small exchanges on the step's critical path (measured at 8 GPUs: a 12.6 MB tagged gather delayed the 131 KB
-        # query gather from 8 to 70 us), so large gathers take the NCCL collective (NVLS / ring over NVSwitch).
+        # Gathers above MOMA_B200_PEER_GATHER_MAX_BYTES take the NCCL collective instead of the peer-memory kernel (whose
+        # in-band tags double the bytes).  Measured at 8 GPUs on the C3 step (profiles/r02_scaling.txt): NCCL for the
+        # 6.3 MB projection gather was NOT faster end to end (0.331 vs 0.291 ms per step), so the default keeps every
+        # gather that fits the symmetric buffer on the peer kernel; what matters is that large and small exchanges do not
+        # overlap in time (step.py sequences them).
         small = world * x.numel() * x.element_size() <= _PEER_GATHER_MAX_BYTES
         if small and x.is_cuda and x.dtype == torch.float32 and (x.numel() * 4) % 16 == 0:
             from .peer import CH_KEYS, PeerExchange

@@ -17,7 +17,7 @@ from torch import nn
 from . import ops
 
 eps = 1e-7
-_GATHER_PROJECTIONS_MAX_BYTES = int(os.environ.get("MOMA_B200_GATHER_PROJECTIONS_MAX_BYTES", 2 << 20))
+_GATHER_PROJECTIONS_MAX_BYTES = int(os.environ.get("MOMA_B200_GATHER_PROJECTIONS_MAX_BYTES", 1 << 30))
 
 
 class Normalize(nn.Module):
@@ -143,12 +143,13 @@ class Attention(nn.Module):
 
     def forward_rows_gathered(self, x_local, gather, q_start, q_stride, q_count):
         """``forward_rows`` over the concatenation of every rank's ``x_local`` (``gather``: [B, .] -> [W * B, .], e.g.
-        ContrastTrainer._global_gather).  No autograd.  Two schedules, chosen by the bytes that would cross NVLink:
-          * few ranks: every rank projects only its own rows (qkv Linear) and the PROJECTIONS are all-gathered
+        ContrastTrainer._global_gather).  No autograd.  Two schedules:
+          * default: every rank projects only its own rows (qkv Linear) and the PROJECTIONS are all-gathered
             (3C floats per token) -- no rank projects a token twice;
-          * many ranks: the raw tokens are all-gathered (C floats per token, the reference's key gather,
-            learning/contrast_trainer.py:124) and projected locally -- 3x fewer bytes on the wire for one extra small GEMM
-            (at 8 x 512 tokens: 2.1 MB instead of 6.3 MB gathered per rank)."""
+          * above MOMA_B200_GATHER_PROJECTIONS_MAX_BYTES: the raw tokens are all-gathered (C floats per token, the
+            reference's key gather, learning/contrast_trainer.py:124) and projected locally -- 3x fewer bytes on the wire
+            for one extra GEMM over all W x B tokens.  Measured at 8 GPUs (C3): slower end to end (0.338 vs 0.291 ms per
+            step: the extra 4096-token GEMM competes with the critical path), hence not the default."""
         with torch.no_grad():
             if not self._fusable(x_local):
                 return self._composed(gather(x_local))[q_start::q_stride][:q_count]

@@ -19,6 +19,8 @@ Per step (all latency-bound, tiny payloads):
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 import torch.nn.functional as F
@@ -48,6 +50,7 @@ class ShardedMoCo(BaseMoCo):
     default process group."""
 
     is_sharded = True
+    after_query_gather = None      # optional callable, invoked right after the query all-gather has been enqueued
 
     def __init__(self, n_dim, K=65536, T=0.07, mem_name='memory', group=None):
         super().__init__(K, T)
@@ -178,11 +181,16 @@ class ShardedMoCo(BaseMoCo):
                 q_op, dtype, q32, k32, rnd = ops.nce_operands(q_, k_, "bf16" if use_bf16 else "fp32")
                 all_q = torch.empty((W * bsz, D), dtype=q_op.dtype, device=q_.device)
                 dist.all_gather_into_tensor(all_q, q_op.contiguous(), group=group)
+            hook = self.after_query_gather
+            if hook is not None:            # the step's other exchanges are sequenced behind this one (see step.py)
+                hook()
             # 2. local pass over this rank's K / W rows for all n queries, then fold the splits
             queue = shadow if use_bf16 else memory_shard
-            # few K-splits per query tile (many ranks -> many query tiles): the merge of the splits runs in the tail of the
-            # tensor-core kernel (one launch, a handful of L2 round trips) instead of a 4096-CTA merge kernel
-            few_splits = use_bf16 and ops.nce_num_splits(all_q.shape[0], D, queue.shape[0], ops.BF16) <= 8
+            # MOMA_B200_NCE_FUSED=few: with few K-splits per query tile (many ranks -> many query tiles) the merge of the splits
+            # runs in the tail of the tensor-core kernel instead of a separate merge launch.  Measured at 8 GPUs together
+            # with the other schedule changes of round 2: not faster than the separate launch, so off by default
+            few_splits = use_bf16 and os.environ.get("MOMA_B200_NCE_FUSED") == "few" \
+                and ops.nce_num_splits(all_q.shape[0], D, queue.shape[0], ops.BF16) <= 8
             if use_bf16 and (few_splits or ops.nce_fused_enabled(all_q.shape[0], D, queue.shape[0])) \
                     and ops.nce_fused_supported(all_q.shape[0], D, queue.shape[0]):
                 packed = ops.nce_fused_packed(all_q, queue, inv_T)       # pass + merge of the K-splits in ONE launch

@@ -119,6 +119,11 @@ class CriterionStep:
     def _loss_and_backward(self, f_s, k, all_k, feat_s, owned_k=None, enqueue_stream=None, ema_stream=None):
         if enqueue_stream is not None:
             output = self.contrast(q=f_s, k=k, defer_enqueue=True)
+            late = getattr(self, "_late_box", None)
+            if late is not None:                        # the queue branch was launched from inside the forward (see below)
+                self.contrast.after_query_gather = None
+                all_k, owned_k = late.pop("keys")
+                self._late_box = None
         else:
             output = self.contrast(q=f_s, k=k, owned_k=owned_k) if owned_k is not None else \
                 self.contrast(q=f_s, k=k, all_k=all_k)
@@ -160,7 +165,11 @@ class CriterionStep:
         crit, opt = self.crit, self.opt
         main = torch.cuda.current_stream()
         if not hasattr(self, "_side"):
-            self._side = [torch.cuda.Stream(self.dev) for _ in range(3)]
+            # EMA and the queue-attention branch at normal priority; the teacher branch at the priority of the student
+            # chain (the launching stream): whichever of the two is longer is the step's critical path (the teacher's
+            # 2048-wide head at C3, the student's at C2)
+            hi = -1 if os.environ.get("MOMA_B200_TEACHER_PRIORITY", "high") == "high" else 0
+            self._side = [torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev, priority=hi), torch.cuda.Stream(self.dev)]
         s_ema, s_t, s_u = self._side
         s_t.wait_stream(main)
         with torch.cuda.stream(s_t):
@@ -168,10 +177,27 @@ class CriterionStep:
                 self.trainer.momentum_update(crit.embed_s, crit.embed_t, opt.alpha)
             with torch.no_grad():
                 k0 = crit.embed_t(self.feat_t)
-            s_u.wait_stream(s_t)
-            with torch.cuda.stream(s_u):
-                all_k, owned = self._queue_keys(k0)
+            late_queue = self.world > 1 and self.sharded and os.environ.get("MOMA_B200_QUEUE_BRANCH", "sequenced") == "sequenced"
+            all_k = owned = None
+            if not late_queue:
+                s_u.wait_stream(s_t)
+                with torch.cuda.stream(s_u):
+                    all_k, owned = self._queue_keys(k0)
             k = crit.atts_k(k0)
+        if late_queue:
+            # Sharded queue: the queue-attention branch starts with a LARGE exchange (the projections of every rank's keys).
+            # Measured at 8 GPUs: while it is in flight, the small query all-gather on the critical path takes 70 us
+            # instead of 8.  So the branch is launched from a hook that fires right after the query all-gather has been
+            # enqueued, and waits for it: the exchanges of a step run one after the other, the branch still overlaps the
+            # InfoNCE pass and the backward.
+            box = {}
+
+            def launch_queue_branch():
+                s_u.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s_u), torch.no_grad():
+                    box["keys"] = self._queue_keys(k0)
+            self.contrast.after_query_gather = launch_queue_branch
+            self._late_box = box
         f_s = crit.embed_s(self.feat_s)
         f_s = crit.atts_q(f_s)
         ema_late = os.environ.get("MOMA_B200_EMA_FORK", "early") != "early"       # A/B switch (see _loss_and_backward)
