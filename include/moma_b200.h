@@ -297,6 +297,23 @@ int moma_sgd_ema_multi(const void *dev_table, int64_t n_chunks, float lr, float 
 int moma_cls_kd(const float *logit_s, const float *logit_t, const int64_t *labels, int64_t B, int64_t n_cls,
                 float T, float *out3, float *grad_cls, float *grad_div, moma_stream_t stream);
 
+/* K-sharded queue: the exchange of the packed records fused into the merge and combine kernels (protocol and the
+ * peer_bases_dev / ctrl_off / data_off / region_bytes / channel arguments of moma_peer_exchange).
+ * moma_nce_merge_push: folds the K-splits of all n = world * rows_per_rank query rows (ordered by owner rank) and
+ *   stores each merged record straight into the receive region of the rank that owns the query.
+ * moma_nce_combine_poll: polls the `world` records of each of this rank's B rows in the local receive region, adds the
+ *   positive column and emits loss rows / dq / flags (as moma_nce_combine_packed); advances the channel's epoch.
+ * Every rank calls both, in this order, on the same channel, once per step; D % 4 == 0, D <= 512. */
+int moma_nce_merge_push(const float *part_m, const float *part_l, const float *part_mmax, const float *part_O,
+                        int n_parts, int64_t rows_per_rank, int64_t D, const uint64_t *peer_bases_dev,
+                        int64_t ctrl_off, int64_t data_off, int64_t region_bytes, int rank, int world, int channel,
+                        moma_stream_t stream);
+int moma_nce_combine_poll(const float *q_f32, const float *kpos_f32, int64_t B, int64_t D, float inv_T,
+                          int round_bf16, float dq_scale, const uint64_t *peer_bases_dev, int64_t ctrl_off,
+                          int64_t data_off, int64_t region_bytes, int rank, int world, int channel,
+                          float *loss_rows, float *dq_unit, int32_t *pos_is_max, float *max_logit,
+                          float *loss_mean, float *acc_pct, moma_stream_t stream);
+
 /* ------------------------------------------------------------------------- *
  * debug / test hooks (not used by the product path)
  * moma_debug_nce_tc: the tcgen05 partial kernel with an optional dump of the raw
@@ -322,6 +339,18 @@ int moma_debug_set_pdl(int enable);
 /* Launch-overhead probe: an empty kernel of `ctas` x `threads` with `smem_bytes` of dynamic shared memory, optionally
  * allocating / releasing all TMEM columns (the launch shape of the InfoNCE kernel, without its work). */
 int moma_debug_probe_launch(int ctas, int threads, int smem_bytes, int use_tmem, int pdl, moma_stream_t stream);
+
+/* The tcgen05 3xTF32 GEMM of csrc/gemm_tc.cu on its own (tests): C[M,N] = act((A o (mask > 0)) . B + bias) with
+ * A stored [M,K] (a_mn = 0) or [K,M] (a_mn = 1) and B stored [N,K] (b_mn = 0) or [K,N] (b_mn = 1); lda / ldb are the
+ * row strides of the stored matrices; a_mn = 1 with b_mn = 0 is not built.  mask (nullable) has A's stored shape and
+ * stride.  workspace from
+ * moma_debug_gemm_tc_workspace_bytes (zero-filled before first use; NULL = no split-K).  MOMA_ERR_UNSUPPORTED for
+ * shapes the kernel does not take (M < 128, unaligned strides). */
+int moma_debug_gemm_tc(const float *A, int64_t lda, int a_mn, const float *mask, const float *B, int64_t ldb, int b_mn,
+                       const float *bias, float *C, int64_t ldc, int64_t M, int64_t N, int64_t K, int relu,
+                       void *workspace, size_t workspace_bytes, moma_stream_t stream);
+size_t moma_debug_gemm_tc_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int moma_debug_gemm_tc_error(void);
 
 #ifdef __cplusplus
 }

@@ -44,6 +44,9 @@ SIGNATURES = {
                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "moma_nce_merge": (c_int, [_vp, _vp, _vp, _vp, c_int, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "moma_nce_merge_packed": (c_int, [_vp, _vp, _vp, _vp, c_int, _i64, _i64, _vp, _vp]),
+    "moma_nce_merge_push": (c_int, [_vp, _vp, _vp, _vp, c_int, _i64, _i64, _vp, _i64, _i64, _i64, c_int, c_int, c_int, _vp]),
+    "moma_nce_combine_poll": (c_int, [_vp, _vp, _i64, _i64, c_float, c_int, c_float, _vp, _i64, _i64, _i64, c_int, c_int, c_int,
+                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "moma_nce_combine_packed": (c_int, [_vp, c_int, _vp, _vp, _i64, _i64, c_float, c_int, c_float,
                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "moma_nce_fused_supported": (c_int, [_i64, _i64, _i64]),
@@ -60,6 +63,9 @@ SIGNATURES = {
     "moma_debug_flops": (ctypes.c_double, [c_int, c_int]),
     "moma_debug_set_pdl": (c_int, [c_int]),
     "moma_debug_probe_launch": (c_int, [c_int, c_int, c_int, c_int, c_int, _vp]),
+    "moma_debug_gemm_tc": (c_int, [_vp, _i64, c_int, _vp, _vp, _i64, c_int, _vp, _vp, _i64, _i64, _i64, _i64, c_int, _vp, c_size_t, _vp]),
+    "moma_debug_gemm_tc_workspace_bytes": (c_size_t, [_i64, _i64, _i64]),
+    "moma_debug_gemm_tc_error": (c_int, []),
     "moma_attn_fwd_rows": (c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, c_int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "moma_attn_bwd_workspace_bytes": (c_size_t, [_i64, _i64, c_int]),
     "moma_attn_bwd": (c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, c_int,

@@ -45,6 +45,12 @@ void note_flops(int kind, double flops);   // algorithmic-FLOP counters behind m
 // gemm.cu: C[M,N] = act(A B^T + bias) on the tensor cores (3xTF32); see the file header for the operand convention
 int gemm_splits(int M, int N, int K);
 size_t gemm_workspace_bytes(int M, int N, int K);
+// tcgen05 3xTF32 GEMM (gemm_tc.cu); gemm_nt dispatches to it
+bool gemm_tc_supported(const float* A, long long lda, const float* B, long long ldb, int M, int N, int K);
+size_t gemm_tc_workspace_bytes(int M, int N, int K);
+int gemm_tc(const float* A, long long lda, int a_mn, const float* mask, long long ldm, const float* B, long long ldb, int b_mn,
+            const float* bias, float* C, long long ldc, int M, int N, int K, int relu, void* workspace, size_t workspace_bytes,
+            cudaStream_t st);
 int gemm_nt(const float* A, const float* a_mask, int64_t a_rs, int64_t a_cs, const float* Bm, int64_t b_rs, int64_t b_cs,
             const float* bias, float* C, int64_t ldc, int M, int N, int K, int relu, void* workspace, size_t workspace_bytes,
             cudaStream_t st, void* c_bf16 = nullptr);     // c_bf16: optional dense [M, N] bf16 copy of C
@@ -132,5 +138,29 @@ __device__ __forceinline__ void st_stream(float4* p, const float4& v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+
+// ---- peer-memory exchange protocol (csrc/peer.cu; also spoken by the InfoNCE merge / combine kernels, csrc/nce_simt.cu)
+constexpr int kPeerMaxWorld = 16, kPeerChannels = 4, kPeerThreads = 256;
+// A peer may legitimately be late by a host-side hiccup (graph instantiation, allocator growth): wait ~30 s of SM clocks
+// before declaring it dead -- long enough for that, short enough that a lost rank becomes an error instead of a hang.
+constexpr long long kPeerTimeoutClk = 60000000000ll;
+
+struct PeerCtrl {
+    unsigned long long epoch[kPeerChannels];
+    unsigned int ticket_done[kPeerChannels];
+};
+// One channel of the symmetric allocation as a kernel argument (bases: device array of every rank's base address)
+struct PeerLink {
+    const unsigned long long* bases;
+    long long ctrl_off, data_off, region_bytes;
+    int rank, world, channel, rows_per_rank;
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ uint4 ld_volatile16(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+#endif
 
 }  // namespace moma

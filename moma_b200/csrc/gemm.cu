@@ -339,11 +339,16 @@ int gemm_splits(int M, int N, int K) {
     return s < 1 ? 1 : s;
 }
 
-size_t gemm_workspace_bytes(int M, int N, int K) {
+static size_t gemm_simt_workspace_bytes(int M, int N, int K) {
     const int s = gemm_splits(M, N, K);
     if (s == 1) return 0;
     const size_t tiles = (size_t)((M + kTM - 1) / kTM) * ((N + kTN - 1) / kTN);
     return ((tiles * sizeof(unsigned) + 255) / 256) * 256 + (size_t)s * M * N * sizeof(float);
+}
+// either kernel may end up running the shape (the choice also depends on pointers and strides): size for both
+size_t gemm_workspace_bytes(int M, int N, int K) {
+    const size_t a = gemm_simt_workspace_bytes(M, N, K), b = M >= 128 ? gemm_tc_workspace_bytes(M, N, K) : 0;
+    return a > b ? a : b;
 }
 
 // workspace == nullptr forces a single split (no workspace needed).  The first `tiles` words of the workspace are the
@@ -351,6 +356,14 @@ size_t gemm_workspace_bytes(int M, int N, int K) {
 int gemm_nt(const float* A, const float* a_mask, int64_t a_rs, int64_t a_cs, const float* Bm, int64_t b_rs, int64_t b_cs,
             const float* bias, float* C, int64_t ldc, int M, int N, int K, int relu, void* workspace, size_t workspace_bytes,
             cudaStream_t st, void* c_bf16) {
+    // tcgen05 kernel (gemm_tc.cu) for tall-enough outputs with TMA-compatible operands
+    if (c_bf16 == nullptr && (a_cs == 1 || a_rs == 1) && (b_cs == 1 || b_rs == 1)) {
+        const int a_mn = (a_cs != 1), b_mn = (b_cs != 1);
+        const long long lda = a_mn ? a_cs : a_rs, ldb = b_mn ? b_cs : b_rs;
+        if (!(a_mn && !b_mn) && gemm_tc_supported(A, lda, Bm, ldb, M, N, K) && (a_mask == nullptr || aligned16(a_mask)) &&
+            (!a_mn || M % 4 == 0) && (!b_mn || N % 4 == 0))
+            return gemm_tc(A, lda, a_mn, a_mask, lda, Bm, ldb, b_mn, bias, C, ldc, M, N, K, relu, workspace, workspace_bytes, st);
+    }
     note_flops(0, 2.0 * M * N * K);
     GemmParams p;
     p.a = Operand{A, a_rs, a_cs, M, operand_mode(A, a_mask, a_rs, a_cs, M, K)};
@@ -360,7 +373,7 @@ int gemm_nt(const float* A, const float* a_mask, int64_t a_rs, int64_t a_cs, con
     if (workspace != nullptr) {
         const int s = gemm_splits(M, N, K);
         if (s > 1) {
-            MOMA_REQUIRE(workspace_bytes >= gemm_workspace_bytes(M, N, K) && aligned16(workspace), MOMA_ERR_WORKSPACE,
+            MOMA_REQUIRE(workspace_bytes >= gemm_simt_workspace_bytes(M, N, K) && aligned16(workspace), MOMA_ERR_WORKSPACE,
                          "gemm: workspace too small or unaligned");
             const size_t tiles = (size_t)((M + kTM - 1) / kTM) * ((N + kTN - 1) / kTN);
             p.splits = s;

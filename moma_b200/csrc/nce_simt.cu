@@ -199,27 +199,72 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
+template <bool kShared>
+__device__ __forceinline__ float4 ld_part(const float* p) {       // partial O: L2-resident global memory, or staged in shared memory
+    if (kShared) return *reinterpret_cast<const float4*>(p);
+    return __ldg(reinterpret_cast<const float4*>(p));
+}
+
 // kFinal: add the positive column and emit loss / dq / flags; otherwise emit one merged partial.
-template <bool kFinal>
+// kPeer (K-sharded queue): the exchange between the ranks happens INSIDE the two kernels, in the protocol of
+// csrc/peer.cu -- no exchange launch between them:
+//   merge  (!kFinal): the merged record [O | m | l | mmax | pad] of global query row r is stored straight into the
+//                     receive region of the rank that owns the query (r / rows_per_rank), as (word, epoch tag) cells;
+//   combine (kFinal): polls the `world` records of its row in the local receive region into shared memory and folds
+//                     them; the last CTA advances the channel's epoch.
+template <bool kFinal, bool kPeer>
 __global__ void __launch_bounds__(kCombThreads)
-nce_reduce_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l,
-                  const float* __restrict__ part_mmax, const float* __restrict__ part_O, int n_parts,
+nce_reduce_kernel(const float* __restrict__ part_m_, const float* __restrict__ part_l_,
+                  const float* __restrict__ part_mmax_, const float* __restrict__ part_O_, int n_parts,
                   const float* __restrict__ q, const float* __restrict__ kpos, int B, int D, float inv_T,
                   int round_bf16, float dq_scale,
-                  int64_t st_ss /* stats stride between parts */, int64_t st_rs /* ... between rows */,
-                  int64_t o_ss /* O stride between parts */, int64_t o_rs /* ... between rows */,
+                  int64_t st_ss_ /* stats stride between parts */, int64_t st_rs_ /* ... between rows */,
+                  int64_t o_ss_ /* O stride between parts */, int64_t o_rs_ /* ... between rows */,
                   int64_t out_rs /* merged-partial output: row stride of the stats (1 = separate arrays) */,
                   int64_t out_o_rs /* row stride of the O output */,
                   float* __restrict__ out_a /* loss_rows | out_m */, float* __restrict__ out_O /* dq | out_O */,
                   int32_t* __restrict__ pos_is_max, float* __restrict__ out_b /* max_logit | out_l */,
-                  float* __restrict__ out_c /* - | out_mmax */) {
+                  float* __restrict__ out_c /* - | out_mmax */, const PeerLink link) {
     pdl_wait();
     pdl_launch_dependents();
     __shared__ float red[4];
     __shared__ float s_w[kCombChunk];
     __shared__ __align__(16) float s_o[4][kCombMaxD];
+    extern __shared__ __align__(16) float s_in[];                  // kPeer && kFinal: [world][D + 4] received records
     const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* kr = kFinal ? kpos + (int64_t)row * D : nullptr;
+    const float *part_m = part_m_, *part_l = part_l_, *part_mmax = part_mmax_, *part_O = part_O_;
+    int64_t st_ss = st_ss_, st_rs = st_rs_, o_ss = o_ss_, o_rs = o_rs_;
+
+    PeerCtrl* ctrl = nullptr;
+    unsigned long long epoch = 0ull;
+    long long region = 0;
+    if (kPeer) {
+        ctrl = reinterpret_cast<PeerCtrl*>(link.bases[link.rank] + link.ctrl_off);
+        epoch = *reinterpret_cast<volatile unsigned long long*>(&ctrl->epoch[link.channel]) + 1ull;
+        region = link.data_off + (2ll * link.channel + (long long)(epoch & 1ull)) * link.region_bytes;
+    }
+    const uint32_t tag = (uint32_t)epoch;
+    const int cells = (D + 4) / 2;                                 // 16-byte (w0, tag, w1, tag) cells per record
+    if (kPeer && kFinal) {
+        // poll this row's record from every rank: slot s of the local region holds the rows_per_rank records rank s pushed
+        const uint4* in = reinterpret_cast<const uint4*>(link.bases[link.rank] + region);
+        const long long t0 = clock64();
+        for (int i = tid; i < link.world * cells; i += kCombThreads) {
+            const int s = i / cells, c = i - s * cells;
+            const uint4* cell = in + ((long long)s * link.rows_per_rank + row) * cells + c;
+            uint4 v = ld_volatile16(cell);
+            while (v.y != tag || v.w != tag) {
+                if (clock64() - t0 > kPeerTimeoutClk) __trap();
+                v = ld_volatile16(cell);
+            }
+            s_in[s * (D + 4) + 2 * c] = __uint_as_float(v.x);
+            s_in[s * (D + 4) + 2 * c + 1] = __uint_as_float(v.z);
+        }
+        __syncthreads();
+        part_O = s_in; part_m = s_in + D; part_l = s_in + D + 1; part_mmax = s_in + D + 2;
+        st_ss = o_ss = D + 4; st_rs = o_rs = 0;
+    }
 
     float pos = 0.f;
     if (kFinal) {
@@ -270,7 +315,7 @@ nce_reduce_kernel(const float* __restrict__ part_m, const float* __restrict__ pa
                         float4 v[8];
 #pragma unroll
                         for (int u = 0; u < 8; ++u)
-                            v[u] = __ldg(reinterpret_cast<const float4*>(Op + (int64_t)(s + 4 * u) * sstride + d));
+                            v[u] = ld_part<kPeer && kFinal>(Op + (int64_t)(s + 4 * u) * sstride + d);
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
                             const float w = s_w[s + 4 * u];
@@ -279,7 +324,7 @@ nce_reduce_kernel(const float* __restrict__ part_m, const float* __restrict__ pa
                         }
                     }
                     for (; s < cnt; s += 4) {
-                        const float4 v = __ldg(reinterpret_cast<const float4*>(Op + (int64_t)s * sstride + d));
+                        const float4 v = ld_part<kPeer && kFinal>(Op + (int64_t)s * sstride + d);
                         const float w = s_w[s];
                         acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
                         acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
@@ -302,10 +347,26 @@ nce_reduce_kernel(const float* __restrict__ part_m, const float* __restrict__ pa
             if (kFinal) {
                 const float kv = round_bf16 ? bf16_round(kr[d0 + d]) : kr[d0 + d];
                 out_O[(int64_t)row * out_o_rs + d0 + d] = ((ov + wpos * kv) / l_tot - kv) * inv_T * dq_scale;
+            } else if (kPeer) {
+                s_o[0][d] = ov;                                    // (this thread is the only reader of column d)
             } else {
                 out_O[(int64_t)row * out_o_rs + d0 + d] = ov;
             }
         }
+    }
+    if (kPeer && !kFinal) {
+        // push the record (D <= kCombMaxD: one pass) to the owner of the query, as tagged cells
+        __syncthreads();
+        const int owner = row / link.rows_per_rank, local = row - owner * link.rows_per_rank;
+        uint4* dst = reinterpret_cast<uint4*>(link.bases[owner] + region) + ((long long)link.rank * link.rows_per_rank + local) * cells;
+        for (int c = tid; c < cells; c += kCombThreads) {
+            float w0, w1;
+            if (2 * c < D) { w0 = s_o[0][2 * c]; w1 = s_o[0][2 * c + 1]; }
+            else if (2 * c == D) { w0 = mref; w1 = l_tot; }
+            else { w0 = mtrue; w1 = 0.f; }
+            dst[c] = make_uint4(__float_as_uint(w0), tag, __float_as_uint(w1), tag);
+        }
+        return;
     }
     if (tid == 0) {
         if (kFinal) {
@@ -314,6 +375,13 @@ nce_reduce_kernel(const float* __restrict__ part_m, const float* __restrict__ pa
             if (out_b) out_b[row] = fmaxf(pos, mtrue);
         } else {
             out_a[row * out_rs] = mref; out_b[row * out_rs] = l_tot; out_c[row * out_rs] = mtrue;
+        }
+    }
+    if (kPeer && kFinal) {
+        __syncthreads();
+        if (tid == 0 && atomicAdd(&ctrl->ticket_done[link.channel], 1u) == gridDim.x - 1u) {   // every CTA has read the epoch
+            ctrl->ticket_done[link.channel] = 0u;
+            *reinterpret_cast<volatile unsigned long long*>(&ctrl->epoch[link.channel]) = epoch;
         }
     }
 }
@@ -472,9 +540,9 @@ extern "C" __attribute__((visibility("default"))) int moma_nce_combine(const flo
     MOMA_REQUIRE(part_m && part_l && part_mmax && part_O && q_f32 && kpos_f32 && loss_rows && dq_unit && pos_is_max,
                  MOMA_ERR_INVALID, "nce_combine: null pointer");
     MOMA_REQUIRE(D % 4 == 0 && aligned16(part_O), MOMA_ERR_ALIGN, "nce_combine: D %% 4 != 0 or part_O unaligned");
-    launch_pdl(nce_reduce_kernel<true>, dim3((unsigned)B), dim3(kCombThreads), 0, as_stream(stream),
+    launch_pdl(nce_reduce_kernel<true, false>, dim3((unsigned)B), dim3(kCombThreads), 0, as_stream(stream),
         part_m, part_l, part_mmax, part_O, n_parts, q_f32, kpos_f32, (int)B, (int)D, inv_T, round_bf16, dq_scale,
-        B, 1, B * D, D, 1, D, loss_rows, dq_unit, pos_is_max, max_logit, nullptr);
+        B, 1, B * D, D, 1, D, loss_rows, dq_unit, pos_is_max, max_logit, nullptr, PeerLink{});
     MOMA_CUDA_LAUNCH_CHECK("nce_combine");
     note_launches(1);
     if (loss_mean && acc_pct) {
@@ -492,9 +560,9 @@ extern "C" __attribute__((visibility("default"))) int moma_nce_merge(
     MOMA_REQUIRE(part_m && part_l && part_mmax && part_O && out_m && out_l && out_mmax && out_O,
                  MOMA_ERR_INVALID, "nce_merge: null pointer");
     MOMA_REQUIRE(D % 4 == 0 && aligned16(part_O), MOMA_ERR_ALIGN, "nce_merge: D %% 4 != 0 or part_O unaligned");
-    launch_pdl(nce_reduce_kernel<false>, dim3((unsigned)B), dim3(kCombThreads), 0, as_stream(stream),
+    launch_pdl(nce_reduce_kernel<false, false>, dim3((unsigned)B), dim3(kCombThreads), 0, as_stream(stream),
         part_m, part_l, part_mmax, part_O, n_parts, nullptr, nullptr, (int)B, (int)D, 1.f, 0, 1.f,
-        B, 1, B * D, D, 1, D, out_m, out_O, nullptr, out_l, out_mmax);
+        B, 1, B * D, D, 1, D, out_m, out_O, nullptr, out_l, out_mmax, PeerLink{});
     MOMA_CUDA_LAUNCH_CHECK("nce_merge");
     note_launches(1);
     return MOMA_OK;
@@ -509,9 +577,9 @@ extern "C" __attribute__((visibility("default"))) int moma_nce_merge_packed(
     MOMA_REQUIRE(part_m && part_l && part_mmax && part_O && packed, MOMA_ERR_INVALID, "nce_merge_packed: null pointer");
     MOMA_REQUIRE(D % 4 == 0 && aligned16(part_O) && aligned16(packed), MOMA_ERR_ALIGN, "nce_merge_packed: alignment");
     const int64_t P = D + 4;
-    launch_pdl(nce_reduce_kernel<false>, dim3((unsigned)B), dim3(kCombThreads), 0, as_stream(stream),
+    launch_pdl(nce_reduce_kernel<false, false>, dim3((unsigned)B), dim3(kCombThreads), 0, as_stream(stream),
         part_m, part_l, part_mmax, part_O, n_parts, nullptr, nullptr, (int)B, (int)D, 1.f, 0, 1.f,
-        B, 1, B * D, D, P, P, packed + D, packed, nullptr, packed + D + 1, packed + D + 2);
+        B, 1, B * D, D, P, P, packed + D, packed, nullptr, packed + D + 1, packed + D + 2, PeerLink{});
     MOMA_CUDA_LAUNCH_CHECK("nce_merge_packed");
     note_launches(1);
     return MOMA_OK;
@@ -526,10 +594,61 @@ extern "C" __attribute__((visibility("default"))) int moma_nce_combine_packed(
                  "nce_combine_packed: null pointer");
     MOMA_REQUIRE(D % 4 == 0 && aligned16(packed), MOMA_ERR_ALIGN, "nce_combine_packed: alignment");
     const int64_t P = D + 4;
-    launch_pdl(nce_reduce_kernel<true>, dim3((unsigned)B), dim3(kCombThreads), 0, as_stream(stream),
+    launch_pdl(nce_reduce_kernel<true, false>, dim3((unsigned)B), dim3(kCombThreads), 0, as_stream(stream),
         packed + D, packed + D + 1, packed + D + 2, packed, n_parts, q_f32, kpos_f32, (int)B, (int)D, inv_T,
-        round_bf16, dq_scale, B * P, P, B * P, P, 1, D, loss_rows, dq_unit, pos_is_max, max_logit, nullptr);
+        round_bf16, dq_scale, B * P, P, B * P, P, 1, D, loss_rows, dq_unit, pos_is_max, max_logit, nullptr, PeerLink{});
     MOMA_CUDA_LAUNCH_CHECK("nce_combine_packed");
+    note_launches(1);
+    if (loss_mean && acc_pct) {
+        launch_pdl(nce_finalize_kernel, dim3(1), dim3(256), 0, as_stream(stream), loss_rows, pos_is_max, (int)B, loss_mean, acc_pct);
+        MOMA_CUDA_LAUNCH_CHECK("nce_finalize");
+        note_launches(1);
+    }
+    return MOMA_OK;
+}
+
+// ---- K-sharded queue: merge + push / poll + combine (the exchange of the packed records runs inside the two kernels)
+// peer_bases_dev / ctrl_off / data_off / region_bytes / channel: as moma_peer_exchange.  n = world * rows_per_rank query
+// rows (ordered by owner rank); every rank calls merge_push, then combine_poll, on the same channel, once per step.
+extern "C" __attribute__((visibility("default"))) int moma_nce_merge_push(
+    const float* part_m, const float* part_l, const float* part_mmax, const float* part_O, int n_parts, int64_t rows_per_rank,
+    int64_t D, const uint64_t* peer_bases_dev, int64_t ctrl_off, int64_t data_off, int64_t region_bytes, int rank, int world,
+    int channel, moma_stream_t stream) {
+    MOMA_REQUIRE(rows_per_rank > 0 && D > 0 && n_parts > 0, MOMA_ERR_INVALID, "nce_merge_push: bad shape");
+    MOMA_REQUIRE(part_m && part_l && part_mmax && part_O && peer_bases_dev, MOMA_ERR_INVALID, "nce_merge_push: null pointer");
+    MOMA_REQUIRE(D % 4 == 0 && D <= kCombMaxD && aligned16(part_O), MOMA_ERR_ALIGN, "nce_merge_push: D %% 4 != 0, D > %d or part_O unaligned", kCombMaxD);
+    MOMA_REQUIRE(world >= 1 && world <= kPeerMaxWorld && rank >= 0 && rank < world && channel >= 0 && channel < kPeerChannels,
+                 MOMA_ERR_INVALID, "nce_merge_push: bad rank / world / channel");
+    MOMA_REQUIRE(2 * rows_per_rank * (D + 4) * 4 * world <= region_bytes && region_bytes % 16 == 0 && data_off % 16 == 0,
+                 MOMA_ERR_WORKSPACE, "nce_merge_push: receive region too small");
+    const int64_t B = rows_per_rank * world;
+    const PeerLink link{reinterpret_cast<const unsigned long long*>(peer_bases_dev), (long long)ctrl_off, (long long)data_off,
+                        (long long)region_bytes, rank, world, channel, (int)rows_per_rank};
+    launch_pdl(nce_reduce_kernel<false, true>, dim3((unsigned)B), dim3(kCombThreads), 0, as_stream(stream),
+        part_m, part_l, part_mmax, part_O, n_parts, nullptr, nullptr, (int)B, (int)D, 1.f, 0, 1.f,
+        B, 1, B * D, D, 1, D, nullptr, nullptr, nullptr, nullptr, nullptr, link);
+    MOMA_CUDA_LAUNCH_CHECK("nce_merge_push");
+    note_launches(1);
+    return MOMA_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int moma_nce_combine_poll(
+    const float* q_f32, const float* kpos_f32, int64_t B, int64_t D, float inv_T, int round_bf16, float dq_scale,
+    const uint64_t* peer_bases_dev, int64_t ctrl_off, int64_t data_off, int64_t region_bytes, int rank, int world, int channel,
+    float* loss_rows, float* dq_unit, int32_t* pos_is_max, float* max_logit, float* loss_mean, float* acc_pct,
+    moma_stream_t stream) {
+    MOMA_REQUIRE(B > 0 && D > 0, MOMA_ERR_INVALID, "nce_combine_poll: bad shape");
+    MOMA_REQUIRE(q_f32 && kpos_f32 && loss_rows && dq_unit && pos_is_max && peer_bases_dev, MOMA_ERR_INVALID, "nce_combine_poll: null pointer");
+    MOMA_REQUIRE(D % 4 == 0 && D <= kCombMaxD, MOMA_ERR_ALIGN, "nce_combine_poll: D %% 4 != 0 or D > %d", kCombMaxD);
+    MOMA_REQUIRE(world >= 1 && world <= kPeerMaxWorld && rank >= 0 && rank < world && channel >= 0 && channel < kPeerChannels,
+                 MOMA_ERR_INVALID, "nce_combine_poll: bad rank / world / channel");
+    const PeerLink link{reinterpret_cast<const unsigned long long*>(peer_bases_dev), (long long)ctrl_off, (long long)data_off,
+                        (long long)region_bytes, rank, world, channel, (int)B};
+    const size_t smem = (size_t)world * (D + 4) * sizeof(float);
+    launch_pdl(nce_reduce_kernel<true, true>, dim3((unsigned)B), dim3(kCombThreads), smem, as_stream(stream),
+        nullptr, nullptr, nullptr, nullptr, world, q_f32, kpos_f32, (int)B, (int)D, inv_T, round_bf16, dq_scale,
+        0, 0, 0, 0, 1, D, loss_rows, dq_unit, pos_is_max, max_logit, nullptr, link);
+    MOMA_CUDA_LAUNCH_CHECK("nce_combine_poll");
     note_launches(1);
     if (loss_mean && acc_pct) {
         launch_pdl(nce_finalize_kernel, dim3(1), dim3(256), 0, as_stream(stream), loss_rows, pos_is_max, (int)B, loss_mean, acc_pct);

@@ -24,21 +24,6 @@ namespace moma {
 
 namespace {
 
-constexpr int kPeerMaxWorld = 16, kPeerChannels = 4, kPeerThreads = 256;
-// A peer may legitimately be late by a host-side hiccup (graph instantiation, allocator growth): wait ~30 s of SM clocks
-// before declaring it dead -- long enough for that, short enough that a lost rank becomes an error instead of a hang.
-constexpr long long kPeerTimeoutClk = 60000000000ll;
-
-struct PeerCtrl {
-    unsigned long long epoch[kPeerChannels];
-    unsigned int ticket_done[kPeerChannels];
-};
-
-__device__ __forceinline__ uint4 ld_volatile16(const uint4* p) {
-    uint4 v;
-    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);

@@ -255,6 +255,34 @@ def nce_combine_packed(packed: torch.Tensor, q_f32: torch.Tensor, k_f32: torch.T
     return rows, dq, pim, mx, fin[0], fin[1:2]
 
 
+def nce_merge_push(stats: torch.Tensor, O: torch.Tensor, peer, channel: int) -> None:
+    """K-sharded queue: fold the split partials of all W * B_local query rows and store each merged record straight into
+    the receive region of the rank that owns the query (``peer``: moma_b200.peer.PeerExchange)."""
+    n_parts, n = stats.shape[1], stats.shape[2]
+    D = O.shape[2]
+    check(_lib.load().moma_nce_merge_push(_p(stats[0]), _p(stats[1]), _p(stats[2]), _p(O), n_parts, n // peer.world, D,
+                                          *peer.link(channel, 2 * n * (D + 4) * 4), _stream()))
+    peer.note_use(channel)
+
+
+def nce_combine_poll(peer, channel: int, q_f32: torch.Tensor, k_f32: torch.Tensor, inv_T: float, round_bf16: bool,
+                     dq_scale: float):
+    """Counterpart of ``nce_merge_push``: poll this rank's records from every rank, add the positive column ->
+    (rows, dq, pos_is_max, max_logit, loss_mean, acc_pct) as ``nce_combine_packed``."""
+    B, D = q_f32.shape
+    dev = q_f32.device
+    rows = torch.empty(B, dtype=torch.float32, device=dev)
+    dq = torch.empty((B, D), dtype=torch.float32, device=dev)
+    pim = torch.empty(B, dtype=torch.int32, device=dev)
+    mx = torch.empty(B, dtype=torch.float32, device=dev)
+    fin = torch.empty(2, dtype=torch.float32, device=dev)
+    check(_lib.load().moma_nce_combine_poll(_p(q_f32), _p(k_f32), B, D, inv_T, int(round_bf16), float(dq_scale),
+                                            *peer.link(channel, 2 * peer.world * B * (D + 4) * 4),
+                                            _p(rows), _p(dq), _p(pim), _p(mx), _p(fin), fin.data_ptr() + 4, _stream()))
+    peer.note_use(channel)
+    return rows, dq, pim, mx, fin[0], fin[1:2]
+
+
 # ---- one-launch InfoNCE (tcgen05 pass + in-kernel combine) ---------------------------------------------------------
 _FUSE_COUNTERS = {}
 

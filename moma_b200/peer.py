@@ -117,22 +117,39 @@ class PeerExchange:
         return sorted(set(cls._status.values()))
 
     # ---------------------------------------------------------------- collectives
-    def _run(self, src, stride_bytes, bytes_per_rank, cast, channel, out):
-        if 2 * bytes_per_rank * self.world > self.region_bytes:          # 8-byte (word, tag) cells: 2x the payload
-            raise RuntimeError("PeerExchange: message larger than the receive region")
-        # a channel is one epoch sequence: its calls must be ordered.  If this call comes from another stream than
-        # the channel's previous call, order it behind that call (inside a capture the step's own fork/join does it)
+    def _order(self, channel):
+        """A channel is one epoch sequence: its calls must be ordered.  If this call comes from another stream than the
+        channel's previous call, order it behind that call (inside a capture the step's own fork/join does it)."""
         cur = torch.cuda.current_stream()
         last = self._last_use.get(channel)
         if last is not None and last[0] != cur.cuda_stream and not torch.cuda.is_current_stream_capturing():
             cur.wait_event(last[1])
-        check(_lib.load().moma_peer_exchange(src.data_ptr(), stride_bytes, bytes_per_rank, int(cast), self.bases_dev,
-                                             0, self.ctrl_bytes, self.region_bytes, self.rank, self.world, channel,
-                                             out.data_ptr(), cur.cuda_stream))
+        return cur
+
+    def note_use(self, channel):
         if not torch.cuda.is_current_stream_capturing():
+            cur = torch.cuda.current_stream()
             ev = torch.cuda.Event()
             ev.record(cur)
             self._last_use[channel] = (cur.cuda_stream, ev)
+
+    def link(self, channel: int, cell_bytes: int):
+        """The C-ABI arguments (peer_bases_dev, ctrl_off, data_off, region_bytes, rank, world, channel) of one channel for
+        kernels that speak the exchange protocol themselves (ops.nce_merge_push / nce_combine_poll).  ``cell_bytes``: the
+        bytes one call writes into a receive region (tagged cells: twice the payload)."""
+        if cell_bytes > self.region_bytes:
+            raise RuntimeError("PeerExchange: message larger than the receive region")
+        self._order(channel)
+        return (self.bases_dev, 0, self.ctrl_bytes, self.region_bytes, self.rank, self.world, channel)
+
+    def _run(self, src, stride_bytes, bytes_per_rank, cast, channel, out):
+        if 2 * bytes_per_rank * self.world > self.region_bytes:          # 8-byte (word, tag) cells: 2x the payload
+            raise RuntimeError("PeerExchange: message larger than the receive region")
+        cur = self._order(channel)
+        check(_lib.load().moma_peer_exchange(src.data_ptr(), stride_bytes, bytes_per_rank, int(cast), self.bases_dev,
+                                             0, self.ctrl_bytes, self.region_bytes, self.rank, self.world, channel,
+                                             out.data_ptr(), cur.cuda_stream))
+        self.note_use(channel)
         return out
 
     def allgather(self, x: torch.Tensor, channel: int, to_bf16: bool = False) -> torch.Tensor:

@@ -196,6 +196,12 @@ class ShardedMoCo(BaseMoCo):
                 packed = ops.nce_fused_packed(all_q, queue, inv_T)       # pass + merge of the K-splits in ONE launch
             else:
                 stats, Opart = ops.nce_partial(all_q, queue, inv_T, dtype)
+                if peer is not None and D <= 512 and os.environ.get("MOMA_B200_PEER_FUSED", "1") != "0":
+                    # 3 + 4 without an exchange launch: the merge kernel stores each record straight into its owner's
+                    # receive region, the combine kernel polls its rows there
+                    ops.nce_merge_push(stats, Opart, peer, CH_PARTIALS)
+                    rows, dq, pim, mx, loss, acc = ops.nce_combine_poll(peer, CH_PARTIALS, q32, k32, inv_T, rnd, 1.0 / bsz)
+                    return loss, rows, pim, mx, acc, dq
                 packed = ops.nce_merge_packed(stats, Opart)             # [n, D + 4] = (O | m | l | mmax | pad)
             # 3. exchange: rows are ordered by owner rank, so the records route with one all-to-all
             if peer is not None:
