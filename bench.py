@@ -268,8 +268,9 @@ FAMILIES = [
     ("nce_tc", r"nce_tc\d?_kernel"),
     ("nce_combine", r"nce_reduce_kernel|nce_finalize_kernel"),
     ("gemm3xtf32", r"gemm3xtf32_kernel"),
+    ("gemm_tc", r"gemm_tc_kernel"),
     ("colsum", r"colsum"),
-    ("attn_fwd", r"attn_fwd_kernel|attn_fwd_tc_kernel|attn_probs"),
+    ("attn_fwd", r"attn_fwd_kernel|attn_fwd_tc_kernel|attn_fwd_splitkv_kernel|attn_probs"),
     ("attn_bwd", r"attn_bwd_|attn_delta"),
     ("fused_head", r"head_fwd_kernel|head_bwd_kernel"),
     ("ema", r"ema_multi_kernel"),

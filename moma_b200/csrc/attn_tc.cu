@@ -223,6 +223,145 @@ attn_fwd_tc_kernel(const float* __restrict__ qkv, int N, int C, float scale, flo
     }
 }
 
+// ---------------------------------------------------------------------------------------------------- forward, keys split over the warps
+// 16 query rows per CTA; its four warps walk DISJOINT quarters of the key / value tiles (warp w: tiles w, w + 4, ...), each
+// with its own double-buffered tiles in shared memory and no CTA-wide barrier in the loop, and merge their (max, sum, O)
+// through shared memory at the end.  For few query rows against many keys -- the K-sharded queue's owned-rows attention,
+// 512 rows x (W x 512) keys -- the serial chain per warp is a quarter of attn_fwd_tc_kernel's and the grid is 4x larger.
+template <int HD>
+__global__ void __launch_bounds__(128)
+attn_fwd_splitkv_kernel(const float* __restrict__ qkv, int N, int C, float scale, float* __restrict__ o, float* __restrict__ lse,
+                        int q_start, int q_stride, int NQ) {
+    pdl_wait();
+    pdl_launch_dependents();
+    constexpr int LD = HD + 4, KS = HD / 8, NT = HD / 8, V4 = HD / 4;
+    extern __shared__ __align__(16) float smem[];
+    constexpr int STAGE = 2 * kTile * LD;                       // K tile then V tile
+    const int h = blockIdx.y, q0 = blockIdx.x * 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int r_lo = q0 + g, r_hi = r_lo + 8;
+    const int64_t ld3 = 3ll * C;
+    const float* kbase = qkv + C + h * HD;
+    const float* vbase = qkv + 2 * C + h * HD;
+    float* wsm = smem + warp * 2 * STAGE;                       // this warp's two stages
+
+    uint32_t qh[KS][4], ql[KS][4];
+    load_a_rows<HD>(qkv + (int64_t)(q_start + (int64_t)r_lo * q_stride) * ld3 + h * HD,
+                    qkv + (int64_t)(q_start + (int64_t)r_hi * q_stride) * ld3 + h * HD, r_lo < NQ, r_hi < NQ,
+                    scale * kLog2e, t, qh, ql);
+    float oacc[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) { oacc[n][0] = oacc[n][1] = oacc[n][2] = oacc[n][3] = 0.f; }
+    float m_lo = -CUDART_INF_F, m_hi = -CUDART_INF_F, l_lo = 0.f, l_hi = 0.f;
+
+    const int ntiles = (N + kTile - 1) / kTile;
+    auto load_warp_tile = [&](float* dst, int kt) {             // K and V rows [kt * 64, +64) by this warp's 32 lanes
+#pragma unroll
+        for (int i = lane; i < kTile * V4; i += 32) {
+            const int r = i / V4, v = i - r * V4;
+            const bool ok = kt * kTile + r < N;
+            const int64_t off = (int64_t)(kt * kTile + r) * ld3 + 4 * v;
+            cp_async16(dst + r * LD + 4 * v, ok ? kbase + off : kbase, ok);
+            cp_async16(dst + kTile * LD + r * LD + 4 * v, ok ? vbase + off : vbase, ok);
+        }
+    };
+    if (warp < ntiles) load_warp_tile(wsm, warp);
+    cp_async_commit();
+    int it = 0;
+    for (int kt = warp; kt < ntiles; kt += 4, ++it) {
+        cp_async_wait<0>();
+        __syncwarp();                                  // tile kt visible to the warp; every lane is done with the previous one
+        if (kt + 4 < ntiles) load_warp_tile(wsm + ((it + 1) & 1) * STAGE, kt + 4);
+        cp_async_commit();
+        const float* K = wsm + (it & 1) * STAGE;
+        const float* V = K + kTile * LD;
+        float s[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                uint32_t bh[2], bl[2];
+                frag_cols<LD>(K, j * 8, ks * 8, g, t, bh, bl);
+                mma3(s[j], qh[ks], ql[ks], bh, bl);
+            }
+        if (kt == ntiles - 1 && (N % kTile) != 0) {     // keys beyond N
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = kt * kTile + j * 8 + 2 * t;
+                if (c >= N) { s[j][0] = -CUDART_INF_F; s[j][2] = -CUDART_INF_F; }
+                if (c + 1 >= N) { s[j][1] = -CUDART_INF_F; s[j][3] = -CUDART_INF_F; }
+            }
+        }
+        float mx_lo = -CUDART_INF_F, mx_hi = -CUDART_INF_F;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            mx_lo = fmaxf(mx_lo, fmaxf(s[j][0], s[j][1]));
+            mx_hi = fmaxf(mx_hi, fmaxf(s[j][2], s[j][3]));
+        }
+        mx_lo = quad_max(mx_lo); mx_hi = quad_max(mx_hi);
+        const float mn_lo = fmaxf(m_lo, mx_lo), mn_hi = fmaxf(m_hi, mx_hi);
+        const float c_lo = ex2f(m_lo - mn_lo), c_hi = ex2f(m_hi - mn_hi);
+        m_lo = mn_lo; m_hi = mn_hi;
+        float sum_lo = 0.f, sum_hi = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            s[j][0] = ex2f(s[j][0] - mn_lo); s[j][1] = ex2f(s[j][1] - mn_lo);
+            s[j][2] = ex2f(s[j][2] - mn_hi); s[j][3] = ex2f(s[j][3] - mn_hi);
+            sum_lo += s[j][0] + s[j][1]; sum_hi += s[j][2] + s[j][3];
+        }
+        l_lo = l_lo * c_lo + sum_lo; l_hi = l_hi * c_hi + sum_hi;
+        float ot[NT][4];
+#pragma unroll
+        for (int n = 0; n < NT; ++n) { ot[n][0] = ot[n][1] = ot[n][2] = ot[n][3] = 0.f; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            uint32_t ph[4], pl[4];
+            acc_to_a(s[j], ph, pl);
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                uint32_t bh[2], bl[2];
+                frag_rows<LD>(V, j * 8, n * 8, g, t, bh, bl);
+                mma3(ot[n], ph, pl, bh, bl);
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            oacc[n][0] = oacc[n][0] * c_lo + ot[n][0]; oacc[n][1] = oacc[n][1] * c_lo + ot[n][1];
+            oacc[n][2] = oacc[n][2] * c_hi + ot[n][2]; oacc[n][3] = oacc[n][3] * c_hi + ot[n][3];
+        }
+    }
+    cp_async_wait<0>();
+    l_lo = quad_sum(l_lo); l_hi = quad_sum(l_hi);
+    // ---- merge the four warps: [warp][16 rows] max / sum and [warp][16][HD] O through shared memory (tiles are dead)
+    __syncthreads();
+    float* sm_m = smem;                                         // [4][16]
+    float* sm_l = smem + 64;                                    // [4][16]
+    float* sm_o = smem + 128;                                   // [4][16][HD]
+    if (t == 0) { sm_m[warp * 16 + g] = m_lo; sm_m[warp * 16 + g + 8] = m_hi; sm_l[warp * 16 + g] = l_lo; sm_l[warp * 16 + g + 8] = l_hi; }
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+        *reinterpret_cast<float2*>(sm_o + (warp * 16 + g) * HD + n * 8 + 2 * t) = make_float2(oacc[n][0], oacc[n][1]);
+        *reinterpret_cast<float2*>(sm_o + (warp * 16 + g + 8) * HD + n * 8 + 2 * t) = make_float2(oacc[n][2], oacc[n][3]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 16 * HD; i += 128) {
+        const int r = i / HD, d = i - r * HD;
+        if (q0 + r >= NQ) continue;
+        const float M = fmaxf(fmaxf(sm_m[r], sm_m[16 + r]), fmaxf(sm_m[32 + r], sm_m[48 + r]));
+        float L = 0.f, O = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const float wgt = ex2f(sm_m[w * 16 + r] - M);      // exp2(-inf) = 0 for a warp that had no tile
+            L += sm_l[w * 16 + r] * wgt;
+            O += sm_o[(w * 16 + r) * HD + d] * wgt;
+        }
+        o[(int64_t)(q0 + r) * C + h * HD + d] = O / L;
+        if (d == 0) lse[(int64_t)h * NQ + q0 + r] = (M + log2f(L)) * kLn2;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------- backward: dQ
 template <int HD>
 __global__ void __launch_bounds__(kThreads)
@@ -434,9 +573,23 @@ static void fwd_w(const float* qkv, int N, int C, int H, float scale, float* o, 
     launch_pdl(attn_fwd_tc_kernel<HD, WARPS>, dim3((NQ + 16 * WARPS - 1) / (16 * WARPS), H), dim3(32 * WARPS), kv_smem<HD>(), st, qkv,
                N, C, scale, o, lse, q_start, q_stride, NQ);
 }
+// keys split over the warps when the query rows are few against the keys (MOMA_B200_ATTN_SPLITKV=0 never, =1 always)
+static bool use_splitkv(int N, int NQ) {
+    static const int mode = [] { const char* e = getenv("MOMA_B200_ATTN_SPLITKV"); return e == nullptr ? -1 : atoi(e); }();
+    if (mode == 0) return false;
+    if (mode == 1) return N >= 4 * kTile;
+    return N >= 16 * kTile && N >= 2 * NQ;
+}
 template <int HD>
 static void fwd(const float* qkv, int N, int C, int H, float scale, float* o, float* lse, cudaStream_t st, int q_start,
                 int q_stride, int NQ) {
+    if (use_splitkv(N, NQ)) {
+        constexpr size_t smem = (size_t)4 * 2 * 2 * kTile * (HD + 4) * sizeof(float);      // 4 warps x 2 stages x (K, V)
+        ensure_dyn_smem(reinterpret_cast<const void*>(attn_fwd_splitkv_kernel<HD>), (int)smem);
+        launch_pdl(attn_fwd_splitkv_kernel<HD>, dim3((NQ + 15) / 16, H), dim3(128), smem, st, qkv, N, C, scale, o, lse, q_start,
+                   q_stride, NQ);
+        return;
+    }
     // 4 warps (64 query rows) per CTA.  Smaller CTAs (2 / 1 warps, more CTAs when rows x heads < SMs) were measured at
     // 8 GPUs on the owned-rows attention (512 rows x 4096 keys): 128 two-warp CTAs took 219 us where 64 four-warp CTAs take
     // 77 us next to the rest of the step -- every CTA streams all K/V tiles, and fewer, fatter CTAs disturb fewer SMs.

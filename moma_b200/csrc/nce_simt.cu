@@ -250,6 +250,21 @@ nce_reduce_kernel(const float* __restrict__ part_m_, const float* __restrict__ p
         // poll this row's record from every rank: slot s of the local region holds the rows_per_rank records rank s pushed
         const uint4* in = reinterpret_cast<const uint4*>(link.bases[link.rank] + region);
         const long long t0 = clock64();
+        // One thread per source rank sleeps on the LAST cell of that rank's record; the other threads park at the barrier.
+        // (All 128 threads of all B CTAs spinning on their own cells was measured at 8 GPUs: lower best-case step, but the
+        // polling traffic slowed the step's other branches -- median 0.315 ms against 0.287 with the separate exchange.)
+        if (tid < link.world) {
+            const uint4* cell = in + ((long long)tid * link.rows_per_rank + row) * cells + (cells - 1);
+            unsigned ns = 32;
+            uint4 v = ld_volatile16(cell);
+            while (v.y != tag || v.w != tag) {
+                __nanosleep(ns);
+                if (ns < 512) ns *= 2;
+                if (clock64() - t0 > kPeerTimeoutClk) __trap();
+                v = ld_volatile16(cell);
+            }
+        }
+        __syncthreads();
         for (int i = tid; i < link.world * cells; i += kCombThreads) {
             const int s = i / cells, c = i - s * cells;
             const uint4* cell = in + ((long long)s * link.rows_per_rank + row) * cells + c;

@@ -73,7 +73,10 @@ peer_exchange_kernel(const void* __restrict__ src, long long src_peer_stride_byt
     const long long t0 = clock64();
     for (long long i = (long long)blockIdx.x * kPeerThreads + threadIdx.x; i < total; i += stride) {
         uint4 c = ld_volatile16(in + i);
+        unsigned ns = 32;
         while (c.y != tag || c.w != tag) {
+            __nanosleep(ns);                                  // back off: the step's other branches share these SMs
+            if (ns < 256) ns *= 2;
             if (clock64() - t0 > kPeerTimeoutClk) { atomicExch(&g_peer_error, 1 + channel); __trap(); }
             c = ld_volatile16(in + i);
         }

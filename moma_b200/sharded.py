@@ -31,6 +31,17 @@ from .peer import CH_PARTIALS, CH_QUERIES, PeerExchange
 from .mem_moco import BaseMoCo, _stale_after_enqueue
 
 
+def _peer_fused(world: int) -> bool:
+    """Exchange fused into the merge / combine kernels (MOMA_B200_PEER_FUSED=1 / 0; default: only for 2 ranks).
+    Measured on B200s, C3 weak: 2 GPUs 0.243 (fused) vs 0.251 ms per step; 8 GPUs 0.317 vs 0.285 -- with 8 ranks the records
+    of one combine CTA come from 8 merge kernels at 8 different points of their own steps, and B polling CTAs wait where
+    the separate exchange kernel waits with at most 37."""
+    env = os.environ.get("MOMA_B200_PEER_FUSED")
+    if env is not None:
+        return env != "0"
+    return world <= 2
+
+
 def cyclic_shard(full: torch.Tensor, rank: int, world: int) -> torch.Tensor:
     """Rows g with g % world == rank, in slot order g // world."""
     return full[rank::world].contiguous()
@@ -196,7 +207,7 @@ class ShardedMoCo(BaseMoCo):
                 packed = ops.nce_fused_packed(all_q, queue, inv_T)       # pass + merge of the K-splits in ONE launch
             else:
                 stats, Opart = ops.nce_partial(all_q, queue, inv_T, dtype)
-                if peer is not None and D <= 512 and os.environ.get("MOMA_B200_PEER_FUSED", "1") != "0":
+                if peer is not None and D <= 512 and _peer_fused(W):
                     # 3 + 4 without an exchange launch: the merge kernel stores each record straight into its owner's
                     # receive region, the combine kernel polls its rows there
                     ops.nce_merge_push(stats, Opart, peer, CH_PARTIALS)

@@ -18,6 +18,6 @@ except Exception as e:
 PY
 }
 run fused X=1
-run unfused MOMA_B200_PEER_FUSED=0
+[ "$N" -le 2 ] && run unfused MOMA_B200_PEER_FUSED=0
 run fused_raw MOMA_B200_GATHER_PROJECTIONS_MAX_BYTES=0
 run fused_raw_early MOMA_B200_GATHER_PROJECTIONS_MAX_BYTES=0 MOMA_B200_QUEUE_BRANCH=early

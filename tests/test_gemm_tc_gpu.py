@@ -78,3 +78,25 @@ def test_linear_dispatches_to_tc_and_matches_fp64():
     y64.backward(g.double())
     for got, ref in ((y, y64), (x.grad, x64.grad), (w.grad, w64.grad), (b.grad, b64.grad)):
         assert float((got.double() - ref).abs().max() / ref.abs().max()) < 2e-6
+
+
+@pytest.mark.parametrize("case", [(2048, 128, 8, 3, 4, 512), (1100, 64, 4, 1, 2, 500), (4096, 128, 8, 5, 8, 512), (1536, 64, 8, 0, 1, 40)])
+def test_attention_rows_keys_split_over_warps(case):
+    """Owned-rows attention with many keys (the split-KV kernel of csrc/attn_tc.cu) against fp64 attention over all
+    tokens, restricted to the same rows."""
+    from moma_b200 import ops
+    N, C, H, q_start, q_stride, q_count = case
+    dev = torch.device("cuda:0")
+    torch.manual_seed(N + C)
+    x = torch.randn(N, C, device=dev)
+    wq, bq = torch.randn(3 * C, C, device=dev) * C ** -0.5, torch.randn(3 * C, device=dev) * 0.1
+    wp, bp = torch.randn(C, C, device=dev) * C ** -0.5, torch.randn(C, device=dev) * 0.1
+    y = ops.attention_rows(x, wq, bq, wp, bp, H, q_start, q_stride, q_count)
+    x64, wq64, bq64, wp64, bp64 = (t.double() for t in (x, wq, bq, wp, bp))
+    qkv = (x64 @ wq64.t() + bq64).reshape(N, 3, H, C // H).permute(1, 2, 0, 3)          # [3, H, N, hd]
+    att = torch.softmax(qkv[0] @ qkv[1].transpose(-1, -2) * (C // H) ** -0.5, dim=-1)
+    ref = ((att @ qkv[2]).transpose(0, 1).reshape(N, C) @ wp64.t() + bp64)[q_start::q_stride][:q_count]
+    assert float((y.double() - ref).abs().max() / ref.abs().max()) < 1e-5
+    qkv32 = (x64 @ wq64.t() + bq64).float()
+    y2 = ops.attention_rows_from_qkv(qkv32, wp, bp, H, q_start, q_stride, q_count)
+    assert float((y2.double() - ref).abs().max() / ref.abs().max()) < 1e-5
