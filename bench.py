@@ -521,13 +521,21 @@ def rooflines(ctx, name, cfg, cs, fam, nce_us, ema_us, gemm_flop, attn_flop, n_s
         e.update(extra or {})
         return e
 
+    # the Linear GEMMs run on two kernels (warp-level below 512^3, tcgen05 from there): one entry for both
+    g_w, g_t = fam.get("gemm3xtf32"), fam.get("gemm_tc")
+    if g_w or g_t:
+        fam = dict(fam)
+        fam["gemm_all"] = {"us": (g_w["us"] if g_w else 0.0) + (g_t["us"] if g_t else 0.0),
+                           "launches": (g_w["launches"] if g_w else 0.0) + (g_t["launches"] if g_t else 0.0)}
     entries = [
         tensor_entry("nce_tc3_kernel (tcgen05 InfoNCE logits + CE forward/backward)", "nce_tc", nce_flop, nce_us,
                      {"traffic": traffic.get("nce_tc3_kernel", traffic.get("nce_tc2_kernel")), "splits": n_splits,
                       "timing": nce_timing, "in_step": "*_in_step: the same kernel inside the replayed step (CUPTI record)"}),
-        tensor_entry("gemm3xtf32_kernel (projection heads + attention projections, 3xTF32 mma.sync)", "gemm3xtf32",
-                     gemm_flop, None, {"note": "algorithmic FLOP counted once (the kernel runs 3 tensor-core passes); "
-                                               "latency-bound launches of <= 0.3 GFLOP each"}),
+        tensor_entry("gemm3xtf32_kernel + gemm_tc_kernel (projection heads + attention projections, 3xTF32: mma.sync below "
+                     "512^3, tcgen05 from there)", "gemm_all",
+                     gemm_flop, None, {"note": "algorithmic FLOP counted once (the kernels run 3 tensor-core passes); "
+                                               "latency-bound launches of <= 0.3 GFLOP each",
+                                       "us_warp_level": g_w["us"] if g_w else 0.0, "us_tcgen05": g_t["us"] if g_t else 0.0}),
     ]
     # attention core: forward and backward families together
     a_f, a_b = fam.get("attn_fwd"), fam.get("attn_bwd")
@@ -548,7 +556,7 @@ def rooflines(ctx, name, cfg, cs, fam, nce_us, ema_us, gemm_flop, attn_flop, n_s
         ema["dram_frac"] = ema["traffic"] / (ema_us * 1e-6) / 1e9 / bw_peak
     entries.append(ema)
     entries.sort(key=lambda e: e.get("us_in_step") or 0.0, reverse=True)
-    total = sum(d["us"] for k_, d in fam.items() if k_ != "attn_core") or 1.0
+    total = sum(d["us"] for k_, d in fam.items() if k_ not in ("attn_core", "gemm_all")) or 1.0
     for e in entries:
         e["share_of_kernel_time"] = (e.get("us_in_step") or 0.0) / total
     return entries
