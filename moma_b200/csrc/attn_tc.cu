@@ -19,7 +19,8 @@
 //   attn_fwd_tc_kernel      O = softmax(Q K^T * scale) V, lse                      (also for a strided subset of the rows)
 //   attn_bwd_dq_tc_kernel   dQ = [P o (dO V^T - delta)] K * scale
 //   attn_bwd_dkv_tc_kernel  dV = P^T dO,  dK = [P o (dO V^T - delta)]^T Q * scale
-// head_dim 8, 16, 32 (all operand fragments of a warp live in registers); larger heads use the SIMT kernels of attn.cu.
+// head_dim 8, 16, 32, 64 (all operand fragments of a warp live in registers; at 64 the dK/dV kernel spills ~0.7 KB per
+// thread and still beats the CUDA-core kernel); head_dim 128 uses the SIMT kernels of attn.cu.
 #include <math_constants.h>
 #include <cstdlib>
 #include <string>
@@ -583,12 +584,14 @@ static bool use_splitkv(int N, int NQ) {
 template <int HD>
 static void fwd(const float* qkv, int N, int C, int H, float scale, float* o, float* lse, cudaStream_t st, int q_start,
                 int q_stride, int NQ) {
-    if (use_splitkv(N, NQ)) {
-        constexpr size_t smem = (size_t)4 * 2 * 2 * kTile * (HD + 4) * sizeof(float);      // 4 warps x 2 stages x (K, V)
-        ensure_dyn_smem(reinterpret_cast<const void*>(attn_fwd_splitkv_kernel<HD>), (int)smem);
-        launch_pdl(attn_fwd_splitkv_kernel<HD>, dim3((NQ + 15) / 16, H), dim3(128), smem, st, qkv, N, C, scale, o, lse, q_start,
-                   q_stride, NQ);
-        return;
+    if constexpr (HD <= 32) {                                   // (head_dim 64: four warps' private tiles exceed shared memory)
+        if (use_splitkv(N, NQ)) {
+            constexpr size_t smem = (size_t)4 * 2 * 2 * kTile * (HD + 4) * sizeof(float);      // 4 warps x 2 stages x (K, V)
+            ensure_dyn_smem(reinterpret_cast<const void*>(attn_fwd_splitkv_kernel<HD>), (int)smem);
+            launch_pdl(attn_fwd_splitkv_kernel<HD>, dim3((NQ + 15) / 16, H), dim3(128), smem, st, qkv, N, C, scale, o, lse, q_start,
+                       q_stride, NQ);
+            return;
+        }
     }
     // 4 warps (64 query rows) per CTA.  Smaller CTAs (2 / 1 warps, more CTAs when rows x heads < SMs) were measured at
     // 8 GPUs on the owned-rows attention (512 rows x 4096 keys): 128 two-warp CTAs took 219 us where 64 four-warp CTAs take
@@ -614,7 +617,8 @@ static void bwd(const float* qkv, const float* dO, const float* lse, const float
 // MOMA_B200_ATTN=simt: the FP32 CUDA-core kernels of attn.cu for every head size (A/B switch, read once)
 bool attn_tc_supported(int hd) {
     static const bool simt = [] { const char* e = getenv("MOMA_B200_ATTN"); return e != nullptr && std::string(e) == "simt"; }();
-    return !simt && (hd == 8 || hd == 16 || hd == 32);
+    static const bool no64 = [] { const char* e = getenv("MOMA_B200_ATTN_TC64"); return e != nullptr && e[0] == '0'; }();
+    return !simt && (hd == 8 || hd == 16 || hd == 32 || (hd == 64 && !no64));
 }
 void attn_tc_fwd(const float* qkv, int N, int C, int H, float scale, float* o, float* lse, cudaStream_t st, int q_start,
                  int q_stride, int NQ) {
@@ -622,6 +626,7 @@ void attn_tc_fwd(const float* qkv, int N, int C, int H, float scale, float* o, f
     switch (C / H) {
         case 8: atc::fwd<8>(qkv, N, C, H, scale, o, lse, st, q_start, q_stride, NQ); break;
         case 16: atc::fwd<16>(qkv, N, C, H, scale, o, lse, st, q_start, q_stride, NQ); break;
+        case 64: atc::fwd<64>(qkv, N, C, H, scale, o, lse, st, q_start, q_stride, NQ); break;
         default: atc::fwd<32>(qkv, N, C, H, scale, o, lse, st, q_start, q_stride, NQ); break;
     }
 }
@@ -631,6 +636,7 @@ void attn_tc_bwd(const float* qkv, const float* dO, const float* lse, const floa
     switch (C / H) {
         case 8: atc::bwd<8>(qkv, dO, lse, delta, N, C, H, scale, dqkv, st, st2); break;
         case 16: atc::bwd<16>(qkv, dO, lse, delta, N, C, H, scale, dqkv, st, st2); break;
+        case 64: atc::bwd<64>(qkv, dO, lse, delta, N, C, H, scale, dqkv, st, st2); break;
         default: atc::bwd<32>(qkv, dO, lse, delta, N, C, H, scale, dqkv, st, st2); break;
     }
 }

@@ -325,7 +325,7 @@ def test_attention_golden(ops, golden, tag):
         assert rel(npy(bq.grad), g[f"{tag}_dbqkv"]) < TOL
 
 
-@pytest.mark.parametrize("N,C,H", [(1, 64, 4), (100, 128, 8), (256, 128, 4), (130, 256, 4), (65, 512, 4)])
+@pytest.mark.parametrize("N,C,H", [(1, 64, 4), (100, 128, 8), (256, 128, 4), (130, 256, 4), (65, 512, 4), (1024, 256, 4)])
 def test_attention_random(ops, N, C, H):
     rng = np.random.default_rng(N + C)
     x = rng.standard_normal((N, C)).astype(np.float32)
