@@ -227,8 +227,9 @@ attn_fwd_tc_kernel(const float* __restrict__ qkv, int N, int C, float scale, flo
 // ---------------------------------------------------------------------------------------------------- forward, keys split over the warps
 // 16 query rows per CTA; its four warps walk DISJOINT quarters of the key / value tiles (warp w: tiles w, w + 4, ...), each
 // with its own double-buffered tiles in shared memory and no CTA-wide barrier in the loop, and merge their (max, sum, O)
-// through shared memory at the end.  For few query rows against many keys -- the K-sharded queue's owned-rows attention,
-// 512 rows x (W x 512) keys -- the serial chain per warp is a quarter of attn_fwd_tc_kernel's and the grid is 4x larger.
+// through shared memory at the end: the serial chain per warp is a quarter of attn_fwd_tc_kernel's and the grid is 4x larger.
+// Used from four key tiles up -- most valuable for few query rows against many keys, the K-sharded queue's owned-rows
+// attention (512 rows x (W x 512) keys).
 template <int HD>
 __global__ void __launch_bounds__(128)
 attn_fwd_splitkv_kernel(const float* __restrict__ qkv, int N, int C, float scale, float* __restrict__ o, float* __restrict__ lse,
@@ -574,12 +575,12 @@ static void fwd_w(const float* qkv, int N, int C, int H, float scale, float* o, 
     launch_pdl(attn_fwd_tc_kernel<HD, WARPS>, dim3((NQ + 16 * WARPS - 1) / (16 * WARPS), H), dim3(32 * WARPS), kv_smem<HD>(), st, qkv,
                N, C, scale, o, lse, q_start, q_stride, NQ);
 }
-// keys split over the warps when the query rows are few against the keys (MOMA_B200_ATTN_SPLITKV=0 never, =1 always)
+// Keys split over the warps from four key tiles up (MOMA_B200_ATTN_SPLITKV=0: never).  Measured on the C3 step: the three
+// N = 512 forward launches 41.8 -> 34.0 us, step 0.1973 -> 0.1938 ms; owned-rows attention at 8 GPUs 131 -> 74 us.
 static bool use_splitkv(int N, int NQ) {
-    static const int mode = [] { const char* e = getenv("MOMA_B200_ATTN_SPLITKV"); return e == nullptr ? -1 : atoi(e); }();
-    if (mode == 0) return false;
-    if (mode == 1) return N >= 4 * kTile;
-    return N >= 16 * kTile && N >= 2 * NQ;
+    static const bool off = [] { const char* e = getenv("MOMA_B200_ATTN_SPLITKV"); return e != nullptr && e[0] == '0'; }();
+    (void)NQ;
+    return !off && N >= 4 * kTile;
 }
 template <int HD>
 static void fwd(const float* qkv, int N, int C, int H, float scale, float* o, float* lse, cudaStream_t st, int q_start,
