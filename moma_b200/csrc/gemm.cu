@@ -361,7 +361,7 @@ int gemm_nt(const float* A, const float* a_mask, int64_t a_rs, int64_t a_cs, con
         const int a_mn = (a_cs != 1), b_mn = (b_cs != 1);
         const long long lda = a_mn ? a_cs : a_rs, ldb = b_mn ? b_cs : b_rs;
         if (!(a_mn && !b_mn) && gemm_tc_supported(A, lda, Bm, ldb, M, N, K) && (a_mask == nullptr || aligned16(a_mask)) &&
-            (!a_mn || M % 4 == 0) && (!b_mn || N % 4 == 0))
+            (a_mn ? M % 4 == 0 : K % 4 == 0) && (b_mn ? N % 4 == 0 : K % 4 == 0))     // float4 along each contiguous dimension
             return gemm_tc(A, lda, a_mn, a_mask, lda, Bm, ldb, b_mn, bias, C, ldc, M, N, K, relu, workspace, workspace_bytes, st);
     }
     note_flops(0, 2.0 * M * N * K);
